@@ -1,0 +1,19 @@
+// fw25_internal.h -- host-side declarations shared by the engine translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include "fw25_kernels.cuh"
+
+namespace fw25 {
+
+// simple (L1/L2-cached) sweeps: fw25_sweeps_simple.cu.  a_lo/a_hi are LOCAL plane indices.
+void launch_sweep_u_simple(int ndim, const Fields &F, const Geom &G, int a_lo, int a_hi, cudaStream_t st);
+void launch_sweep_p_simple(int ndim, const Fields &F, const Geom &G, int a_lo, int a_hi, cudaStream_t st);
+
+// point kernels: fw25_points.cu
+void launch_inject(float *p, const long long *src_idx, const int *src_row, const unsigned char *src_rim,
+                   int n_src, const float *icmat, int nTic, int t, const long long *air_idx, int n_air,
+                   cudaStream_t st);
+void launch_record(const float *p, const long long *sens_idx, int n_sens, float *frame, cudaStream_t st);
+int launches_per_inject(int n_src, int n_air, int t, int nTic, int n_src_rim);
+
+}  // namespace fw25

@@ -1,0 +1,51 @@
+// fw25_kernels.cuh -- shared device-side definitions for the fw25 engine (sm_100a).
+//
+// Arithmetic contract: every floating-point operation is the same single IEEE-754 binary32 operation,
+// in the same order, as the reference's sm_100 cubin (fd_u / fd_p of
+// fullwave2_{2d,3d}_2_relax_isotropic_multi_gpu_sm_100_cuda129; PTX line ranges in SURVEY.md 8(a) and
+// Appendix C; FFMA contraction of the final "q - s*t" taken from the SASS).  The _rn intrinsics are
+// never re-associated or contracted by nvcc/ptxas, so the results are bit-identical to the reference
+// wherever its own operations are (they are all .rn, no .ftz).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace fw25 {
+
+constexpr int M = 8;
+
+__device__ __forceinline__ float fma_(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+__device__ __forceinline__ float mul_(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float add_(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float sub_(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float div_(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float rcp_(float a) { return __frcp_rn(a); }
+
+// Internal layout: every field is [nA][nB][pitch] float32, C (fastest) axis padded to `pitch`
+// (multiple of 4 floats => 16-byte aligned rows for float4 / TMA).  3D: (A,B,C) = (x,y,z).
+// 2D: (A,B,C) = (x,-,y) with nB = 1, i.e. the reference's 2D "y" is our C axis; its v / *y* arrays
+// live in the axis-C slots.
+struct Fields {
+  // medium (read-only)
+  const float *rho, *K, *beta, *kappax, *kappau;
+  const float *ax1, *bx1, *ax2, *bx2;  // apmlx*/bpmlx*: velocity sweep
+  const float *au1, *bu1, *au2, *bu2;  // apmlu*/bpmlu*: pressure sweep
+  const int32_t *dcmap;
+  const float *dmap;                   // [9][2][ndmap]
+  // state
+  float *p;
+  float *q[3];                         // velocity along A,B,C
+  float *psi[3][2];                    // [axis][nu] velocity-sweep memory variables
+  float *phi[3][2];                    // [axis][nu] pressure-sweep memory variables
+};
+
+struct Geom {
+  int nA, nB, nC;       // local planes, rows, points per row
+  int pitch;            // floats per row
+  long long sA, sB;     // strides (floats) of A and B axes; sB == pitch
+  int ndmap;
+  float dX, dT;
+  int a_rim_lo, a_rim_hi; // local A range that may be updated: global [8, nXglobal-8) ∩ owned
+};
+
+}  // namespace fw25

@@ -1,0 +1,54 @@
+// fw25_points.cu -- source injection, air (pressure-release) zeroing and sensor gather.
+// Replaces inject_source (3D PTX L1325-1389), inject_source_zero (L1391-1443),
+// compute_genout_frame_multi (L1477-1570) and extract_pressure_values (L1572-1608): the coordinate ->
+// linear-index maps are resolved once at setup (bit-exact int arithmetic on the host), so the per-step
+// kernels are pure scatter / gather; injection and zeroing share one launch.
+#include "fw25_internal.h"
+
+namespace fw25 {
+
+// p[src] = icmat[row][t] while t < nTic (overwrite, not add); afterwards a source that sits in the
+// never-updated 8-cell rim falls back to 0 (the reference's proceed_time copies the zero new half
+// over it).  Air voxels are zeroed after the sources, as in the reference's launch order.
+__global__ void k_inject(float *__restrict__ p, const long long *__restrict__ src_idx,
+                         const int *__restrict__ src_row, const unsigned char *__restrict__ src_rim,
+                         int n_src, const float *__restrict__ icmat, int nTic, int t) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_src) return;
+  if (t < nTic) p[src_idx[i]] = icmat[(size_t)src_row[i] * nTic + t];
+  else if (src_rim[i]) p[src_idx[i]] = 0.0f;
+}
+
+__global__ void k_zero(float *__restrict__ p, const long long *__restrict__ air_idx, int n_air) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_air) p[air_idx[i]] = 0.0f;
+}
+
+// frame[i] = p'[sensor_i]; sensors in the 8-cell rim (idx < 0) read 0.
+__global__ void k_record(const float *__restrict__ p, const long long *__restrict__ sens_idx, int n_sens,
+                         float *__restrict__ frame) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_sens) return;
+  const long long s = sens_idx[i];
+  frame[i] = s < 0 ? 0.0f : p[s];
+}
+
+int launches_per_inject(int n_src, int n_air, int t, int nTic, int n_src_rim) {
+  int n = 0;
+  if (n_src > 0 && (t < nTic || n_src_rim > 0)) ++n;
+  if (n_air > 0) ++n;
+  return n;
+}
+
+void launch_inject(float *p, const long long *src_idx, const int *src_row, const unsigned char *src_rim,
+                   int n_src, const float *icmat, int nTic, int t, const long long *air_idx, int n_air,
+                   cudaStream_t st) {
+  if (n_src > 0) k_inject<<<(n_src + 255) / 256, 256, 0, st>>>(p, src_idx, src_row, src_rim, n_src, icmat, nTic, t);
+  if (n_air > 0) k_zero<<<(n_air + 255) / 256, 256, 0, st>>>(p, air_idx, n_air);
+}
+
+void launch_record(const float *p, const long long *sens_idx, int n_sens, float *frame, cudaStream_t st) {
+  if (n_sens > 0) k_record<<<(n_sens + 255) / 256, 256, 0, st>>>(p, sens_idx, n_sens, frame);
+}
+
+}  // namespace fw25

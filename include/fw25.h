@@ -1,0 +1,123 @@
+/*
+ * fw25.h -- C-ABI of the B200-native Fullwave 2.5 time-stepping engine (libfw25.so).
+ *
+ * This is the drop-in boundary.  Upstream, `fullwave.Solver.run` reaches the engine by writing a
+ * directory of raw .dat files and exec'ing a pre-compiled CUDA binary:
+ *     /root/reference/fullwave/solver/input_file_writer.py:105-179, :563-881   (the .dat protocol)
+ *     /root/reference/fullwave/solver/launcher.py:160-254                      (subprocess.run + genout.dat)
+ *     /root/reference/fullwave/solver/solver.py:734-759                        (call site)
+ * The reference has no FFI for this path -- the "interface" is that file protocol -- so every entry
+ * point below names the protocol element or reference behaviour it replaces.  INTEGRATION.md shows
+ * the ctypes stub a maintainer would add to fullwave/solver/launcher.py.
+ *
+ * Plain C types only: no torch, no C++ in the signatures.  All arrays are little-endian,
+ * C-contiguous; float maps are float32 over the EXTENDED grid [nX][nY][nZ] (nZ = 1 in 2D),
+ * idx = (x*nY + y)*nZ + z, exactly as the reference writes them (input_file_writer.py:870-881).
+ */
+#ifndef FW25_H
+#define FW25_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FW25_ABI_VERSION 1
+#define FW25_M 8 /* stencil half-width: solver.py:296 (m_spatial_order = 8), kernels launched with M = 8 */
+
+/* One simulation = the contents of one reference "simulation_dir".
+ * Field names are the reference's .dat file stems (input_file_writer.py:766-821, :581-627). */
+typedef struct fw25_problem {
+  int32_t ndim;               /* 2 or 3 (reference: picks the 2d/ or 3d/ binary, solver.py:177-273) */
+  int32_t nX, nY, nZ;         /* nX.dat nY.dat nZ.dat -- planes held by THIS problem (see fw25_slab) */
+  int32_t nT, nTic, modT;     /* nT.dat nTic.dat modT.dat */
+  int32_t ndmap;              /* ndmap.dat */
+  float dX, dT;               /* dX.dat dT.dat (dY, dZ, c0, c.dat, d.dat are read by the reference but unused) */
+  const float *rho, *K, *beta;                    /* rho.dat K.dat beta.dat */
+  const float *kappax, *kappau;                   /* kappax.dat kappau.dat */
+  const float *apmlx1, *bpmlx1, *apmlx2, *bpmlx2; /* feed the velocity sweep (fd_u) */
+  const float *apmlu1, *bpmlu1, *apmlu2, *bpmlu2; /* feed the pressure sweep (fd_p) */
+  const float *dmap;          /* dmap.dat  float32 [9][2][ndmap] */
+  const int32_t *dcmap;       /* dcmap.dat int32   [nX*nY*nZ], 0-based */
+  int32_t ncoords;            /* ncoords.dat */
+  const int32_t *icc;         /* icc.dat   int32 [ncoords][ndim]   rows (x,y[,z]), GLOBAL coordinates */
+  const float *icmat;         /* icmat.dat float32 [ncoords][nTic] */
+  int32_t ncoordsout;         /* ncoordsout.dat */
+  const int32_t *outc;        /* outc.dat  int32 [ncoordsout][ndim], GLOBAL coordinates */
+  int32_t ncoordszero;        /* ncoordszero.dat */
+  const int32_t *icczero;     /* icczero.dat int32 [ncoordszero][ndim], GLOBAL coordinates (air voxels) */
+  /* Extensions (zero = reference behaviour):                                                     */
+  int32_t maps_on_device;     /* 1: the 13 float maps + dcmap are DEVICE pointers on the engine's GPU,
+                                 row pitch == nZ, and are adopted without a copy when nZ % 4 == 0 */
+  float *ext_p, *ext_u, *ext_v, *ext_w; /* optional caller-owned DEVICE state arrays [nX][nY][pitch]
+                                 (pitch = fw25_pitch(nZ)); lets a multi-process driver hand the halo
+                                 planes to NCCL without a copy.  NULL: the engine allocates. */
+} fw25_problem;
+
+/* x-slab owned by one engine when the grid is sharded along x (the reference's slab partitioner,
+ * SURVEY.md 8(e); binary strings "GPU %d: global range [..)").  NULL slab = whole grid. */
+typedef struct fw25_slab {
+  int32_t nX_global;          /* planes of the whole extended grid */
+  int32_t gx0;                /* global x of local plane 0 of the problem's arrays */
+  int32_t own_lo, own_hi;     /* global owned range [own_lo, own_hi); requires
+                                 gx0 <= max(own_lo-8,0) and gx0+nX >= min(own_hi+8, nX_global) */
+} fw25_slab;
+
+typedef struct fw25_stats {
+  double setup_ms;            /* allocation + host->device upload + table preprocessing */
+  double loop_ms;             /* the time loop, device time (CUDA events) */
+  double d2h_ms;              /* genout device->host */
+  int64_t kernel_launches;    /* kernels launched inside the time loop */
+  int64_t h2d_bytes, d2h_bytes;
+  int64_t point_updates;      /* nX*nY*nZ * nT (extended grid, the reference's count) */
+} fw25_stats;
+
+typedef struct fw25_engine fw25_engine; /* opaque */
+
+/* ---- whole-job entry point: replaces `Launcher.run` (launcher.py:160-254) + reading genout.dat.
+ * genout: caller-allocated float32 [ceil(nT/modT)][ncoordsout] == the bytes of genout.dat
+ * (solver.py:600-618 reshapes it to [n_sensors, n_frames]).  device_ids mirrors CUDA_VISIBLE_DEVICES
+ * (launcher.py:63-105, :206): n_devices > 1 shards x-slabs over those GPUs in this process.
+ * Returns 0, or non-zero with fw25_last_error() set (the reference: non-zero exit status ->
+ * SimulationError, launcher.py:221-241). */
+int fw25_run(const fw25_problem *pb, const int32_t *device_ids, int32_t n_devices,
+             float *genout, size_t genout_len, fw25_stats *stats);
+
+/* ---- engine handle: what the reference's `main` does between loading the .dat files and the time
+ * loop, kept alive so a caller can step, read fields and reuse uploads. */
+int fw25_create(const fw25_problem *pb, const fw25_slab *slab, int32_t device, fw25_engine **out);
+void fw25_destroy(fw25_engine *e);
+
+/* One reference time step is: inject(t) -> sweep_u -> sweep_p -> record(t) when t % modT == 0
+ * (SURVEY.md 3.3).  x ranges are GLOBAL and are clamped to the engine's owned range. stream is a
+ * cudaStream_t (NULL = the engine's own stream). */
+int fw25_inject(fw25_engine *e, int32_t t, void *stream);                            /* inject_source + inject_source_zero */
+int fw25_sweep_u(fw25_engine *e, int32_t gx_lo, int32_t gx_hi, void *stream);        /* fd_u */
+int fw25_sweep_p(fw25_engine *e, int32_t gx_lo, int32_t gx_hi, void *stream);        /* fd_p */
+int fw25_record(fw25_engine *e, int32_t frame, void *stream);                        /* compute_genout_frame_multi / extract_pressure_values */
+int fw25_step(fw25_engine *e, int32_t n_steps);  /* n whole steps from the engine's current t, on its own stream */
+int fw25_sync(fw25_engine *e);
+
+/* Results.  fw25_read_frames copies frames [f0, f1) of the owned sensors: out is
+ * [f1-f0][fw25_n_local_sensors]; fw25_local_sensor_ids gives their row in the global outc list. */
+int32_t fw25_n_local_sensors(const fw25_engine *e);
+int fw25_local_sensor_ids(const fw25_engine *e, int32_t *ids);
+int fw25_read_frames(fw25_engine *e, int32_t f0, int32_t f1, float *out);
+/* name: "p","u","v","w"; out: float32 [nX][nY][nZ] of the engine's local planes (tests). */
+int fw25_read_field(fw25_engine *e, const char *name, float *out);
+/* device pointer of a state array ("p","u","v","w") and the row pitch (floats) of its layout */
+void *fw25_field_ptr(fw25_engine *e, const char *name);
+int32_t fw25_pitch(int32_t nZ);
+int32_t fw25_current_step(const fw25_engine *e);
+int64_t fw25_launch_count(const fw25_engine *e);
+/* select the sweep implementation: 0 = auto, 1 = simple (L1/L2-cached loads), 2 = TMA-tiled x-marching */
+int fw25_set_kernel_variant(fw25_engine *e, int32_t variant);
+
+const char *fw25_last_error(void);
+int32_t fw25_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,19 @@
+"""Seeded small problems shared by the CPU and GPU tests (sizes the oracle finishes in < 1 s)."""
+
+from fullwave25_b200 import synthetic
+
+CASES = {
+    # name: (kwargs for synthetic.make_problem)
+    "het3d": dict(shape=(48, 52, 56), nT=60, modT=2, seed=1),
+    "het3d_ragged": dict(shape=(45, 47, 53), nT=40, modT=3, seed=5, n_sensors=37, n_air=5),
+    "het3d_long": dict(shape=(44, 44, 44), nT=300, modT=7, seed=7, n_pml=5, n_trans=3),
+    "hom3d": dict(shape=(44, 46, 48), nT=50, modT=1, seed=3, homogeneous=True, n_air=0),
+    "het2d": dict(shape=(80, 90), nT=200, modT=3, seed=2),
+    "het2d_ragged": dict(shape=(83, 77), nT=150, modT=4, seed=9, n_sensors=50),
+    "het2d_long": dict(shape=(120, 100), nT=1200, modT=5, seed=11),
+    "hom2d": dict(shape=(64, 70), nT=100, modT=1, seed=4, homogeneous=True, n_air=0),
+}
+
+
+def make(name):
+    return synthetic.make_problem(**CASES[name])

@@ -1,0 +1,98 @@
+"""Parity tests proper: the CUDA engine, called through the C-ABI (libfw25.so), against the CPU oracle
+on the same seeded inputs.  Arithmetic is IEEE-identical operation by operation, so the bar is
+BIT-EXACT sensor traces and final fields (the north-star tolerance is rel-L2 <= 1e-5; we assert 0)."""
+
+import numpy as np
+import pytest
+
+from fullwave25_b200 import engine
+from oracle import oracle
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+
+ALL = sorted(cases.CASES)
+
+
+def rel_l2(a, b):
+    d = np.linalg.norm(a.astype(np.float64) - b.astype(np.float64))
+    n = np.linalg.norm(b.astype(np.float64))
+    return d / n if n else d
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_run_matches_oracle_bit_exact(built_lib, name):
+    pb = cases.make(name)
+    want = oracle.run(pb)
+    got, stats = engine.run(pb)
+    assert got.shape == want.shape
+    assert np.isfinite(got).all()
+    assert rel_l2(got, want) <= 1e-5          # the stated FP32 tolerance
+    np.testing.assert_array_equal(got, want)  # and in fact identical bits
+    assert stats["kernel_launches"] >= 2 * pb.nT
+    assert stats["point_updates"] == pb.n_points * pb.nT
+
+
+@pytest.mark.parametrize("name", ["het3d", "het2d", "het3d_ragged"])
+def test_final_fields_match_oracle(built_lib, name):
+    pb = cases.make(name)
+    _, want = oracle.run(pb, return_fields=True)
+    with engine.Engine(pb) as e:
+        e.step(pb.nT)
+        e.sync()
+        for k in ("p", "u", "v") + (("w",) if pb.ndim == 3 else ()):
+            np.testing.assert_array_equal(e.field(k), want[k], err_msg=k)
+
+
+@pytest.mark.parametrize("name", ["het3d", "het2d"])
+def test_piecewise_sweeps_equal_full_sweeps(built_lib, name):
+    """fw25_sweep_u / fw25_sweep_p over sub-ranges (the boundary-first schedule) == whole sweeps."""
+    pb = cases.make(name)
+    nX = pb.nX
+    with engine.Engine(pb) as a, engine.Engine(pb) as b:
+        a.step(15)
+        for t in range(15):
+            b.inject(t)
+            for lo, hi in ((nX - 16, nX), (0, 16), (16, nX - 16)):
+                b.sweep_u(lo, hi)
+            for lo, hi in ((nX // 2, nX), (0, nX // 2)):
+                b.sweep_p(lo, hi)
+            if t % pb.modT == 0:
+                b.record(t // pb.modT)
+        a.sync(); b.sync()
+        for k in ("p", "u", "v"):
+            np.testing.assert_array_equal(a.field(k), b.field(k), err_msg=k)
+        nf = -(-15 // pb.modT)
+        np.testing.assert_array_equal(a.read_frames(0, nf), b.read_frames(0, nf))
+
+
+def test_edge_cases(built_lib):
+    # no sensors, no air, no sources after nTic, nT not a multiple of modT
+    pb = cases.make("het2d_ragged")
+    pb.outc = pb.outc[:0]
+    got, _ = engine.run(pb)
+    assert got.shape == (pb.n_frames, 0)
+    pb = cases.make("het3d_ragged")
+    pb.icczero = pb.icczero[:0]
+    np.testing.assert_array_equal(engine.run(pb)[0], oracle.run(pb))
+    # sensors in the 8-cell rim read 0; duplicate sensors are allowed
+    pb = cases.make("het2d")
+    pb.outc = np.vstack([pb.outc, [[3, 40], [40, 2]], pb.outc[:2]]).astype(np.int32)
+    got = engine.run(pb)[0]
+    np.testing.assert_array_equal(got, oracle.run(pb))
+    assert not got[:, -4:-2].any()
+    # zero steps
+    pb = cases.make("het2d")
+    pb.nT = 0
+    assert engine.run(pb)[0].shape == (0, pb.ncoordsout)
+
+
+def test_errors_are_reported_not_swallowed(built_lib):
+    pb = cases.make("het2d")
+    pb.outc = pb.outc.copy()
+    pb.outc[0, 0] = pb.nX + 5
+    with pytest.raises(engine.EngineError, match="outside the grid"):
+        engine.run(pb)
+    pb = cases.make("het2d")
+    with pytest.raises(engine.EngineError):
+        engine.run(pb, device_ids=(97,))
