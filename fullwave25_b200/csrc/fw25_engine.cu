@@ -70,9 +70,11 @@ struct Engine {
   int64_t launches = 0;
   int variant = 0;
   int64_t h2d_bytes = 0;
+  TiledPlan *plan = nullptr;   // TMA-tiled sweeps (3D)
 
   ~Engine() {
     cudaSetDevice(device);
+    tiled_plan_destroy(plan);
     for (void *p : owned) cudaFree(p);
     if (stream) cudaStreamDestroy(stream);
   }
@@ -97,12 +99,14 @@ struct Engine {
     return (long long)(x - gx0) * G.sA + y;
   }
 
-  const float *upload_map(const float *src, bool on_device) {
-    const int rows = G.nA * G.nB;
-    if (on_device && G.pitch == G.nC) return src;  // adopt
+  // src_pitch: floats per row of the caller's array.  A device array already in the engine's padded layout
+  // is adopted as is (no copy) unless `must_copy`.
+  const float *upload_map(const float *src, bool on_device, int src_pitch, bool must_copy = false) {
+    const size_t rows = (size_t)G.nA * G.nB;
+    if (on_device && src_pitch == G.pitch && !must_copy) return src;
     float *dst = dalloc<float>(cells);
     if (G.pitch != G.nC) FW_CUDA(cudaMemsetAsync(dst, 0, cells * sizeof(float), stream));
-    FW_CUDA(cudaMemcpy2DAsync(dst, (size_t)G.pitch * 4, src, (size_t)G.nC * 4, (size_t)G.nC * 4, rows,
+    FW_CUDA(cudaMemcpy2DAsync(dst, (size_t)G.pitch * 4, src, (size_t)src_pitch * 4, (size_t)G.nC * 4, rows,
                               on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream));
     if (!on_device) h2d_bytes += (int64_t)rows * G.nC * 4;
     return dst;
@@ -134,7 +138,7 @@ struct Engine {
     G.nA = nXl;
     G.nB = ndim == 3 ? nY : 1;
     G.nC = ndim == 3 ? nZ : nY;
-    G.pitch = round_up(G.nC, 4);
+    G.pitch = round_up(G.nC, 32);   // 128-byte rows: one warp = one line, TMA-legal strides
     G.sB = G.pitch;
     G.sA = (long long)G.nB * G.pitch;
     G.ndmap = pb.ndmap;
@@ -144,21 +148,31 @@ struct Engine {
     cells = (size_t)G.nA * G.nB * G.pitch;
 
     const bool dev_maps = pb.maps_on_device != 0;
+    const int mp = pb.map_pitch > 0 ? pb.map_pitch : G.nC;
+    if (mp < G.nC) fail(1, "map_pitch is smaller than the fastest axis");
     const float *maps[13] = {pb.rho, pb.K, pb.beta, pb.kappax, pb.kappau, pb.apmlx1, pb.bpmlx1,
                              pb.apmlx2, pb.bpmlx2, pb.apmlu1, pb.bpmlu1, pb.apmlu2, pb.bpmlu2};
     for (auto m : maps)
       if (!m) fail(1, "a medium map pointer is NULL");
     if (!pb.dmap || !pb.dcmap) fail(1, "dmap / dcmap pointer is NULL");
-    F.rho = upload_map(pb.rho, dev_maps);
-    F.K = upload_map(pb.K, dev_maps);
-    F.beta = upload_map(pb.beta, dev_maps);
-    F.kappax = upload_map(pb.kappax, dev_maps);
-    F.kappau = upload_map(pb.kappau, dev_maps);
-    F.ax1 = upload_map(pb.apmlx1, dev_maps); F.bx1 = upload_map(pb.bpmlx1, dev_maps);
-    F.ax2 = upload_map(pb.apmlx2, dev_maps); F.bx2 = upload_map(pb.bpmlx2, dev_maps);
-    F.au1 = upload_map(pb.apmlu1, dev_maps); F.bu1 = upload_map(pb.bpmlu1, dev_maps);
-    F.au2 = upload_map(pb.apmlu2, dev_maps); F.bu2 = upload_map(pb.bpmlu2, dev_maps);
-    F.dcmap = reinterpret_cast<const int32_t *>(upload_map(reinterpret_cast<const float *>(pb.dcmap), dev_maps));
+    F.rho = upload_map(pb.rho, dev_maps, mp);
+    F.K = upload_map(pb.K, dev_maps, mp);
+    F.beta = upload_map(pb.beta, dev_maps, mp);
+    F.kappax = upload_map(pb.kappax, dev_maps, mp);
+    F.kappau = upload_map(pb.kappau, dev_maps, mp);
+    F.ax1 = upload_map(pb.apmlx1, dev_maps, mp); F.bx1 = upload_map(pb.bpmlx1, dev_maps, mp);
+    F.ax2 = upload_map(pb.apmlx2, dev_maps, mp); F.bx2 = upload_map(pb.bpmlx2, dev_maps, mp);
+    F.au1 = upload_map(pb.apmlu1, dev_maps, mp); F.bu1 = upload_map(pb.bpmlu1, dev_maps, mp);
+    F.au2 = upload_map(pb.apmlu2, dev_maps, mp); F.bu2 = upload_map(pb.bpmlu2, dev_maps, mp);
+    {
+      // Reference 3D behaviour: only the first nX*nY entries of dcmap are honoured (fw25.h, dcmap_full3d).
+      const bool mask = ndim == 3 && !pb.dcmap_full3d;
+      int32_t *dc = const_cast<int32_t *>(reinterpret_cast<const int32_t *>(
+          upload_map(reinterpret_cast<const float *>(pb.dcmap), dev_maps, mp, /*must_copy=*/mask)));
+      if (mask)
+        launch_dcmap_mask(dc, (long long)cells, G.pitch, G.nC, G.nB, gx0, (long long)nX_global * nY, stream);
+      F.dcmap = dc;
+    }
     {
       float *d = dalloc<float>((size_t)18 * pb.ndmap);
       // dmap is a small host table in both modes
@@ -183,6 +197,14 @@ struct Engine {
         F.psi[ax][nu] = used ? state(nullptr) : nullptr;
         F.phi[ax][nu] = used ? state(nullptr) : nullptr;
       }
+
+    if (tiled_supported(ndim, G)) {
+      std::string perr;
+      std::vector<float> hd((size_t)18 * pb.ndmap);
+      memcpy(hd.data(), pb.dmap, hd.size() * 4);
+      plan = tiled_plan_create(F, G, hd.data(), stream, &perr);
+      if (!plan) fail(2, "tiled sweep setup failed: " + perr);
+    }
 
     // ---- coordinate lists -> linear indices (bit-exact integer maps)
     const int nd = ndim;
@@ -259,6 +281,8 @@ struct Engine {
     FW_CUDA(cudaStreamSynchronize(stream));
   }
 
+  bool use_tiled() const { return plan != nullptr && variant != 1; }
+
   void clamp(int gx_lo, int gx_hi, int &a_lo, int &a_hi) const {
     a_lo = std::max(gx_lo - gx0, G.a_rim_lo);
     a_hi = std::min(gx_hi - gx0, G.a_rim_hi);
@@ -273,6 +297,7 @@ struct Engine {
     int a_lo, a_hi;
     clamp(gx_lo, gx_hi, a_lo, a_hi);
     if (a_hi <= a_lo) return;
+    if (use_tiled()) { launches += launch_sweep_u_tiled(plan, F, G, a_lo, a_hi, st); return; }
     launch_sweep_u_simple(ndim, F, G, a_lo, a_hi, st);
     launches += (a_hi - a_lo + 32767) / 32768;
   }
@@ -280,6 +305,7 @@ struct Engine {
     int a_lo, a_hi;
     clamp(gx_lo, gx_hi, a_lo, a_hi);
     if (a_hi <= a_lo) return;
+    if (use_tiled()) { launches += launch_sweep_p_tiled(plan, F, G, a_lo, a_hi, st); return; }
     launch_sweep_p_simple(ndim, F, G, a_lo, a_hi, st);
     launches += (a_hi - a_lo + 32767) / 32768;
   }
@@ -342,7 +368,7 @@ extern "C" {
 
 const char *fw25_last_error(void) { return g_err.c_str(); }
 int32_t fw25_abi_version(void) { return FW25_ABI_VERSION; }
-int32_t fw25_pitch(int32_t n_fast) { return fw25::round_up(n_fast, 4); }
+int32_t fw25_pitch(int32_t n_fast) { return fw25::round_up(n_fast, 32); }
 
 int fw25_create(const fw25_problem *pb, const fw25_slab *slab, int32_t device, fw25_engine **out) {
   if (!pb || !out) { g_err = "fw25_create: NULL argument"; return 1; }
@@ -406,7 +432,12 @@ int fw25_read_field(fw25_engine *h, const char *name, float *out) {
 void *fw25_field_ptr(fw25_engine *h, const char *name) { return h->e.field(name); }
 int32_t fw25_current_step(const fw25_engine *h) { return h->e.t; }
 int64_t fw25_launch_count(const fw25_engine *h) { return h->e.launches; }
-int fw25_set_kernel_variant(fw25_engine *h, int32_t v) { h->e.variant = v; return 0; }
+int fw25_set_kernel_variant(fw25_engine *h, int32_t v) {
+  if (v < 0 || v > 2) { g_err = "fw25_set_kernel_variant: variant must be 0, 1 or 2"; return 1; }
+  if (v == 2 && !h->e.plan) { g_err = "fw25_set_kernel_variant: the TMA-tiled sweeps need a 3D problem"; return 1; }
+  h->e.variant = v;
+  return 0;
+}
 
 int fw25_run(const fw25_problem *pb, const int32_t *device_ids, int32_t n_devices, float *genout,
              size_t genout_len, fw25_stats *stats) {

@@ -1,6 +1,7 @@
 // fw25_internal.h -- host-side declarations shared by the engine translation units.
 #pragma once
 #include <cuda_runtime.h>
+#include <string>
 #include "fw25_kernels.cuh"
 
 namespace fw25 {
@@ -9,7 +10,17 @@ namespace fw25 {
 void launch_sweep_u_simple(int ndim, const Fields &F, const Geom &G, int a_lo, int a_hi, cudaStream_t st);
 void launch_sweep_p_simple(int ndim, const Fields &F, const Geom &G, int a_lo, int a_hi, cudaStream_t st);
 
+// TMA-tiled x-marching sweeps (3D): fw25_sweeps_tiled.cu.  Return the number of kernels launched.
+struct TiledPlan;
+bool tiled_supported(int ndim, const Geom &G);
+TiledPlan *tiled_plan_create(const Fields &F, const Geom &G, const float *host_dmap, cudaStream_t st, std::string *err);
+void tiled_plan_destroy(TiledPlan *pl);
+int launch_sweep_u_tiled(const TiledPlan *pl, const Fields &F, const Geom &G, int a_lo, int a_hi, cudaStream_t st);
+int launch_sweep_p_tiled(const TiledPlan *pl, const Fields &F, const Geom &G, int a_lo, int a_hi, cudaStream_t st);
+
 // point kernels: fw25_points.cu
+void launch_dcmap_mask(int32_t *dcmap, long long cells, int pitch, int nC, int nB, long long first_plane,
+                       long long limit, cudaStream_t st);
 void launch_inject(float *p, const long long *src_idx, const int *src_row, const unsigned char *src_rim,
                    int n_src, const float *icmat, int nTic, int t, const long long *air_idx, int n_air,
                    cudaStream_t st);

@@ -3,6 +3,8 @@
 // compute_genout_frame_multi (L1477-1570) and extract_pressure_values (L1572-1608): the coordinate ->
 // linear-index maps are resolved once at setup (bit-exact int arithmetic on the host), so the per-step
 // kernels are pure scatter / gather; injection and zeroing share one launch.
+#include <algorithm>
+
 #include "fw25_internal.h"
 
 namespace fw25 {
@@ -31,6 +33,27 @@ __global__ void k_record(const float *__restrict__ p, const long long *__restric
   if (i >= n_sens) return;
   const long long s = sens_idx[i];
   frame[i] = s < 0 ? 0.0f : p[s];
+}
+
+// Reference 3D behaviour (include/fw25.h, dcmap_full3d): entries whose flat index in the WHOLE dense grid
+// ((x*nY + y)*nZ + z) is >= limit (= nX*nY) read 0.  Runs once at setup on the engine's padded copy.
+__global__ void k_dcmap_mask(int32_t *__restrict__ dc, long long cells, int pitch, int nC, int nB,
+                             long long first_plane, long long limit) {
+  for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < cells;
+       j += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(j % pitch);
+    const long long row = j / pitch;
+    const int b = (int)(row % nB);
+    const long long a = row / nB + first_plane;
+    const long long flat = (a * nB + b) * nC + c;
+    if (c < nC && flat >= limit) dc[j] = 0;
+  }
+}
+
+void launch_dcmap_mask(int32_t *dcmap, long long cells, int pitch, int nC, int nB, long long first_plane,
+                       long long limit, cudaStream_t st) {
+  const int blocks = (int)std::min<long long>((cells + 255) / 256, 148LL * 16);
+  k_dcmap_mask<<<blocks, 256, 0, st>>>(dcmap, cells, pitch, nC, nB, first_plane, limit);
 }
 
 int launches_per_inject(int n_src, int n_air, int t, int nTic, int n_src_rim) {

@@ -37,7 +37,7 @@ class CProblem(C.Structure):
         ("ncoords", C.c_int32), ("icc", C.c_void_p), ("icmat", C.c_void_p),
         ("ncoordsout", C.c_int32), ("outc", C.c_void_p),
         ("ncoordszero", C.c_int32), ("icczero", C.c_void_p),
-        ("maps_on_device", C.c_int32),
+        ("maps_on_device", C.c_int32), ("map_pitch", C.c_int32), ("dcmap_full3d", C.c_int32),
         ("ext_p", C.c_void_p), ("ext_u", C.c_void_p), ("ext_v", C.c_void_p), ("ext_w", C.c_void_p),
     ]
 
@@ -115,11 +115,13 @@ def marshal(pb: Problem, *, device_maps: dict | None = None, ext_state: dict | N
     s.ndim, s.nX, s.nY, s.nZ = pb.ndim, pb.nX, pb.nY, pb.nZ if pb.ndim == 3 else 1
     s.nT, s.nTic, s.modT, s.ndmap = pb.nT, pb.nTic, pb.modT, pb.ndmap
     s.dX, s.dT = pb.dX, pb.dT
+    s.dcmap_full3d = int(bool(pb.dcmap_full3d))
     keep = [pb]
     if device_maps is not None:
         for name in MAP_NAMES + ("dcmap",):
             setattr(s, name, int(device_maps[name]))
         s.maps_on_device = 1
+        s.map_pitch = int(device_maps.get("pitch", 0))
     else:
         for name in MAP_NAMES + ("dcmap",):
             a = getattr(pb, name)

@@ -60,6 +60,9 @@ class Problem:
     outc: np.ndarray            # int32 [ncoordsout, ndim]
     icczero: np.ndarray         # int32 [ncoordszero, ndim]
     extra: dict = field(default_factory=dict)  # dY, dZ, c0, c, d: written by the reference, unused by the engine
+    # False = the reference 3D binary's behaviour: only the first nX*nY entries of dcmap are honoured, the
+    # rest read 0 (include/fw25.h, fw25_problem.dcmap_full3d).  No effect in 2D.
+    dcmap_full3d: bool = False
 
     # ------------------------------------------------------------------ basics
     @property
@@ -233,4 +236,4 @@ class Problem:
         return Problem(ndim=self.ndim, nX=gx1 - gx0, nY=self.nY, nZ=self.nZ, nT=self.nT, nTic=self.nTic,
                        modT=self.modT, ndmap=self.ndmap, dX=self.dX, dT=self.dT, **kw, dmap=self.dmap,
                        dcmap=self.dcmap[gx0:gx1], icc=self.icc, icmat=self.icmat, outc=self.outc,
-                       icczero=self.icczero, extra={})
+                       icczero=self.icczero, extra={}, dcmap_full3d=self.dcmap_full3d)

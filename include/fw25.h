@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define FW25_ABI_VERSION 1
+#define FW25_ABI_VERSION 2
 #define FW25_M 8 /* stencil half-width: solver.py:296 (m_spatial_order = 8), kernels launched with M = 8 */
 
 /* One simulation = the contents of one reference "simulation_dir".
@@ -48,8 +48,16 @@ typedef struct fw25_problem {
   int32_t ncoordszero;        /* ncoordszero.dat */
   const int32_t *icczero;     /* icczero.dat int32 [ncoordszero][ndim], GLOBAL coordinates (air voxels) */
   /* Extensions (zero = reference behaviour):                                                     */
-  int32_t maps_on_device;     /* 1: the 13 float maps + dcmap are DEVICE pointers on the engine's GPU,
-                                 row pitch == nZ, and are adopted without a copy when nZ % 4 == 0 */
+  int32_t maps_on_device;     /* 1: the 13 float maps + dcmap are DEVICE pointers on the engine's GPU */
+  int32_t map_pitch;          /* floats per row (fastest axis) of the 13 maps + dcmap; 0 = dense (nZ, or
+                                 nY in 2D).  Device maps with map_pitch == fw25_pitch(n_fast) are
+                                 adopted without a copy (dcmap only when dcmap_full3d != 0). */
+  int32_t dcmap_full3d;       /* 0: what the reference's 3D binary does -- its main() loads only the first
+                                 nX*nY entries of dcmap.dat into a zeroed array (count = nX*nY at ASM
+                                 0x40648c-0x4064c3; c.dat next to it gets nX*nY*nZ), so every 3D voxel
+                                 whose flat index is >= nX*nY uses stencil-table column 0.  Verified
+                                 bit-exactly on a B200 (DESIGN.md "dcmap").  1: honour dcmap per voxel
+                                 (the documented intent; differs from the binary by ~4e-4 rel-L2). */
   float *ext_p, *ext_u, *ext_v, *ext_w; /* optional caller-owned DEVICE state arrays [nX][nY][pitch]
                                  (pitch = fw25_pitch(nZ)); lets a multi-process driver hand the halo
                                  planes to NCCL without a copy.  NULL: the engine allocates. */
@@ -111,7 +119,8 @@ void *fw25_field_ptr(fw25_engine *e, const char *name);
 int32_t fw25_pitch(int32_t nZ);
 int32_t fw25_current_step(const fw25_engine *e);
 int64_t fw25_launch_count(const fw25_engine *e);
-/* select the sweep implementation: 0 = auto, 1 = simple (L1/L2-cached loads), 2 = TMA-tiled x-marching */
+/* select the sweep implementation: 0 = auto, 1 = simple (L1/L2-cached loads), 2 = TMA-tiled x-marching
+ * (3D only; fails with an error if the variant cannot run the problem) */
 int fw25_set_kernel_variant(fw25_engine *e, int32_t variant);
 
 const char *fw25_last_error(void);

@@ -48,6 +48,9 @@ typedef struct fw25o_problem {
   int32_t ncoords;     const int32_t *icc;     const float *icmat; /* [ncoords][ndim], [ncoords][nTic] */
   int32_t ncoordsout;  const int32_t *outc;    /* [ncoordsout][ndim] */
   int32_t ncoordszero; const int32_t *icczero; /* [ncoordszero][ndim] */
+  int32_t dcmap_full3d;      /* 0: the 3D binary's behaviour (only the first nX*nY dcmap entries are
+                                loaded, the rest read 0 -- see dcmap_3d in fw25_oracle.c); 1: per-voxel */
+  int32_t nX_dcmap;          /* nX of the WHOLE grid for that rule (== nX unless pb is a slab view) */
 } fw25o_problem;
 
 /* state: p,u,v,w + 6 psi (velocity-sweep memory variables: x1,y1,z1,x2,y2,z2) + 6 phi.

@@ -35,6 +35,7 @@ class _Problem(C.Structure):
         ("ncoords", C.c_int32), ("icc", _I), ("icmat", _F),
         ("ncoordsout", C.c_int32), ("outc", _I),
         ("ncoordszero", C.c_int32), ("icczero", _I),
+        ("dcmap_full3d", C.c_int32), ("nX_dcmap", C.c_int32),
     ]
 
 
@@ -50,9 +51,8 @@ _lib = None
 
 def build(force: bool = False) -> None:
     """Compile the oracle with oracle/Makefile (gcc only)."""
-    if force or not (_HERE / "libfw25_oracle.so").exists() or not (_HERE / "libfw25_oracle_fma.so").exists():
-        subprocess.run(["make", "-C", str(_HERE), "-B" if force else "-s"], check=True,
-                       stdout=subprocess.DEVNULL)
+    # make decides staleness (sources newer than the .so) -- cheap when up to date
+    subprocess.run(["make", "-C", str(_HERE), "-B" if force else "-s"], check=True, stdout=subprocess.DEVNULL)
 
 
 def _cpu_has_fma() -> bool:
@@ -100,6 +100,8 @@ def _marshal(pb):
     s.nZ = int(pb.nZ) if pb.ndim == 3 else 1
     s.nT, s.nTic, s.modT, s.ndmap = int(pb.nT), int(pb.nTic), int(pb.modT), int(pb.ndmap)
     s.dX, s.dT = float(pb.dX), float(pb.dT)
+    s.dcmap_full3d = int(bool(getattr(pb, "dcmap_full3d", False)))
+    s.nX_dcmap = s.nX
     n = s.nX * s.nY * s.nZ
     for name in _MAPS:
         a = _f32(getattr(pb, name)).reshape(-1)

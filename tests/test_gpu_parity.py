@@ -33,11 +33,25 @@ def test_run_matches_oracle_bit_exact(built_lib, name):
     assert stats["point_updates"] == pb.n_points * pb.nT
 
 
-@pytest.mark.parametrize("name", ["het3d", "het2d", "het3d_ragged"])
-def test_final_fields_match_oracle(built_lib, name):
+@pytest.mark.parametrize("name", ALL)
+def test_run_matches_reference_golden_bit_exact(built_lib, name):
+    """CUDA engine vs the sensor traces of the reference's own sm_100 binary (tests/golden/ref_*.npz)."""
+    from tests.test_oracle_golden import load_golden
+    want = load_golden(name)
+    got, _ = engine.run(cases.make(name))
+    assert rel_l2(got, want) <= 1e-5
+    np.testing.assert_array_equal(got, want)
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("name", ["het3d", "het2d", "het3d_ragged", "het3d_long"])
+def test_final_fields_match_oracle(built_lib, name, variant):
+    """variant 1 = simple sweeps, 2 = TMA-tiled x-marching sweeps (3D only)."""
     pb = cases.make(name)
+    if variant == 2 and pb.ndim == 2:
+        pytest.skip("tiled sweeps are 3D")
     _, want = oracle.run(pb, return_fields=True)
-    with engine.Engine(pb) as e:
+    with engine.Engine(pb, variant=variant) as e:
         e.step(pb.nT)
         e.sync()
         for k in ("p", "u", "v") + (("w",) if pb.ndim == 3 else ()):
