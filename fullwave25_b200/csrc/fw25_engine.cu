@@ -402,6 +402,46 @@ int fw25_step(fw25_engine *h, int32_t n) {
     FW_CUDA(cudaGetLastError());
   })
 }
+// n whole steps timed with CUDA events on the engine's stream.  out[0] = total ms; with detail != 0 every
+// sweep launch is bracketed too: out[1] = sum over fd_u launches, out[2] = fd_p, out[3] = rest
+// (injection, recording, gaps).  Blocks until the steps are done.
+int fw25_step_timed(fw25_engine *h, int32_t n, int32_t detail, double *out) {
+  FW_TRY({
+    Engine &e = h->e;
+    FW_CUDA(cudaSetDevice(e.device));
+    std::vector<cudaEvent_t> ev((size_t)(detail ? 4 * n : 0) + 2);
+    for (auto &x : ev) FW_CUDA(cudaEventCreate(&x));
+    FW_CUDA(cudaEventRecord(ev[0], e.stream));
+    for (int i = 0; i < n; ++i) {
+      if (!detail) { e.step_once(); continue; }
+      cudaEvent_t *q = &ev[2 + 4 * (size_t)i];
+      e.inject(e.t, e.stream);
+      FW_CUDA(cudaEventRecord(q[0], e.stream));
+      e.sweep_u(0, e.nX_global, e.stream);
+      FW_CUDA(cudaEventRecord(q[1], e.stream));
+      FW_CUDA(cudaEventRecord(q[2], e.stream));
+      e.sweep_p(0, e.nX_global, e.stream);
+      FW_CUDA(cudaEventRecord(q[3], e.stream));
+      if (e.t % e.modT == 0) e.record(e.t / e.modT, e.stream);
+      ++e.t;
+    }
+    FW_CUDA(cudaEventRecord(ev[1], e.stream));
+    FW_CUDA(cudaEventSynchronize(ev[1]));
+    FW_CUDA(cudaGetLastError());
+    float ms = 0;
+    FW_CUDA(cudaEventElapsedTime(&ms, ev[0], ev[1]));
+    out[0] = ms; out[1] = out[2] = out[3] = 0;
+    if (detail) {
+      for (int i = 0; i < n; ++i) {
+        cudaEvent_t *q = &ev[2 + 4 * (size_t)i];
+        FW_CUDA(cudaEventElapsedTime(&ms, q[0], q[1])); out[1] += ms;
+        FW_CUDA(cudaEventElapsedTime(&ms, q[2], q[3])); out[2] += ms;
+      }
+      out[3] = out[0] - out[1] - out[2];
+    }
+    for (auto &x : ev) cudaEventDestroy(x);
+  })
+}
 int fw25_sync(fw25_engine *h) {
   FW_TRY({
     FW_CUDA(cudaSetDevice(h->e.device));

@@ -64,6 +64,7 @@ _SIGS = {
     "fw25_record": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "fw25_step": (C.c_int, [C.c_void_p, C.c_int32]),
     "fw25_sync": (C.c_int, [C.c_void_p]),
+    "fw25_step_timed": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_double)]),
     "fw25_n_local_sensors": (C.c_int32, [C.c_void_p]),
     "fw25_local_sensor_ids": (C.c_int, [C.c_void_p, _I]),
     "fw25_read_frames": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, _F]),
@@ -187,6 +188,12 @@ class Engine:
 
     def step(self, n: int = 1) -> None:
         _check(lib().fw25_step(self._h, n))
+
+    def step_timed(self, n: int, detail: bool = False) -> dict:
+        """n steps timed with CUDA events on the engine's stream -> {total_ms, sweep_u_ms, sweep_p_ms, other_ms}."""
+        out = (C.c_double * 4)()
+        _check(lib().fw25_step_timed(self._h, n, int(detail), out))
+        return {"total_ms": out[0], "sweep_u_ms": out[1], "sweep_p_ms": out[2], "other_ms": out[3]}
 
     def sync(self) -> None:
         _check(lib().fw25_sync(self._h))

@@ -106,6 +106,10 @@ int fw25_sweep_p(fw25_engine *e, int32_t gx_lo, int32_t gx_hi, void *stream);   
 int fw25_record(fw25_engine *e, int32_t frame, void *stream);                        /* compute_genout_frame_multi / extract_pressure_values */
 int fw25_step(fw25_engine *e, int32_t n_steps);  /* n whole steps from the engine's current t, on its own stream */
 int fw25_sync(fw25_engine *e);
+/* n_steps whole steps bracketed by CUDA events on the engine's stream (blocks until done): out[0] = total
+ * ms; detail != 0 also brackets every sweep launch: out[1] = sum fd_u ms, out[2] = sum fd_p ms, out[3] = rest
+ * (the measurement hook behind bench.py's roofline numbers; the reference has no timers). */
+int fw25_step_timed(fw25_engine *e, int32_t n_steps, int32_t detail, double *out4);
 
 /* Results.  fw25_read_frames copies frames [f0, f1) of the owned sensors: out is
  * [f1-f0][fw25_n_local_sensors]; fw25_local_sensor_ids gives their row in the global outc list. */
