@@ -55,25 +55,45 @@ def _stale(target: Path, deps: list[Path]) -> bool:
     return any(d.stat().st_mtime > t for d in deps)
 
 
+def _compile(nvcc: str, src: Path, obj: Path) -> tuple[int, str]:
+    cmd = [nvcc, *NVCC_FLAGS, *_host_cxx(), "-c", "-o", str(obj), str(src)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    return r.returncode, " ".join(cmd) + "\n" + r.stdout + r.stderr
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
-    deps = list(CSRC.glob("*")) + [ROOT / "include" / "fw25.h", Path(__file__)]
+    """Compile every .cu to an object (in parallel), link libfw25.so and the fw25_engine executable."""
+    from concurrent.futures import ThreadPoolExecutor
+    hdrs = list(CSRC.glob("*.h")) + list(CSRC.glob("*.cuh")) + [ROOT / "include" / "fw25.h", Path(__file__)]
     nvcc = _nvcc()
-    if force or _stale(LIB, deps):
-        cmd = [nvcc, *NVCC_FLAGS, *_host_cxx(), "-shared", "-o", str(LIB), *map(str, sources())]
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        (PKG / "build.log").write_text(" ".join(cmd) + "\n" + r.stdout + r.stderr)
-        if r.returncode != 0:
-            sys.stderr.write(r.stdout + r.stderr)
-            raise RuntimeError("nvcc failed building libfw25.so")
+    objdir = PKG / "build"
+    objdir.mkdir(exist_ok=True)
+    srcs = sorted(CSRC.glob("*.cu"))
+    todo = [(s, objdir / (s.stem + ".o")) for s in srcs]
+    stale = [(s, o) for s, o in todo if force or _stale(o, [s, *hdrs])]
+    log = []
+    if stale:
+        with ThreadPoolExecutor(max_workers=min(8, len(stale))) as ex:
+            for (s, o), (rc, out) in zip(stale, ex.map(lambda so: _compile(nvcc, *so), stale)):
+                log.append(out)
+                if rc != 0:
+                    sys.stderr.write(out)
+                    raise RuntimeError(f"nvcc failed on {s.name}")
+        (PKG / "build.log").write_text("\n".join(log))
         if verbose:
-            print(r.stderr)
-    cli_src = CSRC / "fw25_cli.cu"
-    if cli_src.exists() and (force or _stale(CLI, deps)):
-        cmd = [nvcc, *NVCC_FLAGS, *_host_cxx(), "-o", str(CLI), str(cli_src), *map(str, sources())]
-        r = subprocess.run(cmd, capture_output=True, text=True)
+            print("\n".join(log))
+    lib_objs = [str(o) for s, o in todo if s.name != "fw25_cli.cu"]
+    all_objs = [str(o) for _, o in todo]
+    if stale or not LIB.exists():
+        r = subprocess.run([nvcc, *_host_cxx(), "-shared", "-o", str(LIB), *lib_objs], capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
-            raise RuntimeError("nvcc failed building fw25_engine")
+            raise RuntimeError("linking libfw25.so failed")
+    if stale or not CLI.exists():
+        r = subprocess.run([nvcc, *_host_cxx(), "-o", str(CLI), *all_objs], capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("linking fw25_engine failed")
     return LIB
 
 

@@ -1,0 +1,139 @@
+"""Host-side mirror of the reference's launcher layer -- the seam where the new engine plugs in.
+
+Upstream, `fullwave.Solver.run` hands a directory of `.dat` files to
+`fullwave.solver.launcher.Launcher.run` (/root/reference/fullwave/solver/launcher.py:160-254), which
+exec's a pre-compiled CUDA binary there and reads `genout.dat` back.  This module keeps that interface
+(same class name, constructor arguments, `run(simulation_dir, load_results=...)`, `SimulationError`,
+`cuda_device_id` forms None / int / "N" / [ids]) and computes the result with libfw25.so in-process.
+
+Three ways to use it:
+  1. `install()`  -- swap the launcher class inside the reference package: `fullwave.Solver` then runs on
+                     the new engine with no other change (the .dat directory is still written, genout.dat too);
+  2. `run_solver(solver, ...)` -- same result without the disk round trip: the engine input is built
+                     straight from the solver's PML-extended objects;
+  3. the `fw25_engine` executable -- pass it as `Solver(path_fullwave_simulation_bin=...)`; zero edits.
+There is no CPU path: like the reference (`use_gpu=False` raises NotImplementedError, launcher.py:191-194).
+"""
+
+from __future__ import annotations
+
+import logging
+import time
+from pathlib import Path
+
+import numpy as np
+
+from . import engine
+from .problem import Problem
+
+logger = logging.getLogger("__main__." + __name__)
+
+
+class SimulationError(Exception):
+    """Raised when the engine fails (the reference raises its own SimulationError on a non-zero exit status)."""
+
+
+def parse_cuda_device_id(cuda_device_id) -> str:
+    """None -> "0", 3 -> "3", "3" -> "3", [0, 1] -> "0,1"; same errors as launcher.py:63-105."""
+    if cuda_device_id is None:
+        return "0"
+    if isinstance(cuda_device_id, bool):
+        raise ValueError("CUDA device ID must be an integer, string, list, or None.")
+    if isinstance(cuda_device_id, int):
+        if cuda_device_id < 0:
+            raise ValueError("CUDA device ID must be a non-negative integer.")
+        return str(cuda_device_id)
+    if isinstance(cuda_device_id, str):
+        if not cuda_device_id.isdigit() or int(cuda_device_id) < 0:
+            raise ValueError("CUDA device ID string must represent a non-negative integer.")
+        return cuda_device_id
+    if isinstance(cuda_device_id, list):
+        if not all(isinstance(i, int) and not isinstance(i, bool) and i >= 0 for i in cuda_device_id):
+            raise ValueError("All CUDA device IDs in the list must be non-negative integers.")
+        return ",".join(str(i) for i in cuda_device_id)
+    raise ValueError("CUDA device ID must be an integer, string, list, or None.")
+
+
+def device_ids_of(cuda_device_id) -> tuple[int, ...]:
+    return tuple(int(v) for v in parse_cuda_device_id(cuda_device_id).split(","))
+
+
+class Launcher:
+    """Drop-in for `fullwave.solver.launcher.Launcher`, backed by libfw25.so."""
+
+    def __init__(self, path_fullwave_simulation_bin: Path | None = None, *, is_3d: bool = False,
+                 use_gpu: bool = True, cuda_device_id=None) -> None:
+        self._path_fullwave_simulation_bin = path_fullwave_simulation_bin   # kept for interface parity; unused
+        self.is_3d = is_3d
+        self.use_gpu = use_gpu
+        self.cuda_device_id = parse_cuda_device_id(cuda_device_id)
+        self.last_stats: dict | None = None
+        engine.lib()                                                        # fail at construction if not built
+
+    def run(self, simulation_dir: Path, *, load_results: bool = True):
+        simulation_dir = Path(simulation_dir).absolute()
+        if not self.use_gpu:
+            raise NotImplementedError("Currently, only GPU version is supported.")
+        log = simulation_dir / "fw2_execution.log"
+        t0 = time.time()
+        try:
+            pb = Problem.from_dat_dir(simulation_dir)
+            if bool(self.is_3d) != (pb.ndim == 3):
+                raise ValueError(f"launcher is_3d={self.is_3d} but the directory holds a {pb.ndim}D problem")
+            genout, stats = engine.run(pb, device_ids=device_ids_of(self.cuda_device_id))
+        except Exception as e:  # noqa: BLE001
+            log.write_text(f"fw25 engine failed: {type(e).__name__}: {e}\n")
+            msg = ("Simulation failed. please check the simulation log file for more information.\n"
+                   f"The log file is located at:\n{log}")
+            logger.exception(msg)
+            raise SimulationError(msg) from e
+        self.last_stats = stats
+        genout.tofile(simulation_dir / "genout.dat")
+        log.write_text(f"fw25 engine (libfw25.so, sm_100a)\n{stats}\nSimulation completed in {time.time() - t0:.2e} s\n")
+        if not load_results:
+            return simulation_dir / "genout.dat"
+        flat = genout.reshape(-1)
+        if np.isnan(flat).any():
+            logger.warning("The simulation contains NaN values. Check the simulation domains or PML settings.")
+        if np.isinf(flat).any():
+            logger.warning("The simulation contains Inf values. Check the simulation domains or PML settings.")
+        return flat
+
+
+def install(fullwave_module=None):
+    """Make the reference's `Solver` use this launcher: replaces `fullwave.solver.solver.Launcher` (the name
+    `Solver.__init__` instantiates, solver.py:510-515) and `SimulationError`.  Returns an `uninstall` callable."""
+    import importlib
+    sol = importlib.import_module("fullwave.solver.solver")
+    lau = importlib.import_module("fullwave.solver.launcher")
+    saved = (sol.Launcher, lau.Launcher)
+    sol.Launcher = Launcher
+    lau.Launcher = Launcher
+
+    def uninstall():
+        sol.Launcher, lau.Launcher = saved
+    return uninstall
+
+
+def run_solver(solver, *, record_whole_domain: bool = False, sampling_modulus_time_whole_domain: int = 1,
+               cuda_device_id=None, return_stats: bool = False):
+    """`Solver.run` without the disk: PMLBuilder stays the reference's own Python (solver.py:694), the engine
+    input is assembled in memory (what InputFileWriter would have written, input_file_writer.py:563-881) and
+    the sensor traces come back as [n_sensors, n_frames] exactly like `Solver._reshape_sensor_data`."""
+    extended_medium = solver.pml_builder.run(use_pml=solver.use_pml)
+    sensor = solver.pml_builder.extended_sensor
+    if record_whole_domain:
+        import fullwave
+        eg = solver.pml_builder.extended_grid
+        shape = (eg.nx, eg.ny, eg.nz) if solver.is_3d else (eg.nx, eg.ny)
+        sensor = fullwave.Sensor(mask=np.ones(shape, dtype=bool),
+                                 sampling_modulus_time=sampling_modulus_time_whole_domain)
+    pb = Problem.from_fullwave_objects(solver.pml_builder.extended_grid, extended_medium,
+                                       solver.pml_builder.extended_source, sensor)
+    ids = device_ids_of(cuda_device_id if cuda_device_id is not None else getattr(solver, "cuda_device_id", None))
+    try:
+        genout, stats = engine.run(pb, device_ids=ids)
+    except engine.EngineError as e:
+        raise SimulationError(str(e)) from e
+    result = genout.reshape(-1, pb.ncoordsout).T          # solver.py:600-618
+    return (result, stats) if return_stats else result

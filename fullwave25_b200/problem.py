@@ -112,7 +112,8 @@ class Problem:
         self.icc = np.ascontiguousarray(self.icc, dtype=np.int32).reshape(-1, self.ndim)
         self.outc = np.ascontiguousarray(self.outc, dtype=np.int32).reshape(-1, self.ndim)
         self.icczero = np.ascontiguousarray(self.icczero, dtype=np.int32).reshape(-1, self.ndim)
-        self.icmat = np.ascontiguousarray(self.icmat, dtype=np.float32).reshape(self.ncoords, -1)
+        self.icmat = np.ascontiguousarray(self.icmat, dtype=np.float32).reshape(
+            self.ncoords, self.nTic if self.ncoords == 0 else -1)
         if self.ncoords and self.icmat.shape[1] != self.nTic:
             raise ValueError("icmat must be [ncoords, nTic]")
         if self.modT < 1:

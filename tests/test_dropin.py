@@ -1,0 +1,103 @@
+"""Drop-in boundary against the REFERENCE's own Python layer (needs the reference package: /root/reference in the
+build container, baseline/_ref on the GPU box; skipped when neither is present).
+
+CPU: what `Problem.from_fullwave_objects` assembles in memory is byte-identical to the directory the reference's
+`InputFileWriter` writes for the same PML-extended objects, and `Problem.from_dat_dir` reads that directory back.
+GPU: `fullwave.Solver.run` gives identical sensor data with (a) the reference's shipped sm_100 binary, (b) the
+`fw25_engine` executable passed as path_fullwave_simulation_bin, (c) `launcher.install()`, (d) `run_solver`."""
+
+import shutil
+import tempfile
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from fullwave25_b200 import launcher
+from fullwave25_b200.problem import MAP_NAMES, Problem
+
+try:
+    from tools import ref_objects
+    _fw = ref_objects.import_fullwave()
+    HAVE_REF = True
+except Exception:  # noqa: BLE001
+    HAVE_REF = False
+
+needs_ref = pytest.mark.skipif(not HAVE_REF, reason="reference package not available")
+
+
+def _write_with_reference(shape, td, **kw):
+    fw, grid, medium, source, sensor = ref_objects.build(shape, **kw)
+    from fullwave.solver.input_file_writer import InputFileWriter
+    from fullwave.solver.pml_builder import PMLBuilder
+    pml = PMLBuilder(grid=grid, medium=medium, source=source, sensor=sensor, m_spatial_order=8,
+                     n_pml_layer=6, n_transition_layer=4, use_isotropic_relaxation=True)
+    ext = pml.run(use_pml=True)
+    w = InputFileWriter(work_dir=Path(td), grid=pml.extended_grid, medium=ext, source=pml.extended_source,
+                        sensor=pml.extended_sensor, path_fullwave_simulation_bin=ref_objects.ref_bin(len(shape)),
+                        use_exponential_attenuation=False, use_isotropic_relaxation=True)
+    sim_dir = w.run("txrx_0", is_static_map=False, recalculate_pml=True)
+    return pml, ext, Path(sim_dir)
+
+
+@needs_ref
+@pytest.mark.parametrize("shape", [(20, 24), (12, 14, 16)])
+def test_in_memory_problem_equals_reference_dat_directory(shape):
+    with tempfile.TemporaryDirectory() as td:
+        pml, ext, sim_dir = _write_with_reference(shape, td, n_steps=30, n_sensors=9, n_air=5)
+        from_files = Problem.from_dat_dir(sim_dir)
+        in_mem = Problem.from_fullwave_objects(pml.extended_grid, ext, pml.extended_source, pml.extended_sensor)
+    for k in ("ndim", "nX", "nY", "nZ", "nT", "nTic", "modT", "ndmap", "dX", "dT"):
+        assert getattr(from_files, k) == getattr(in_mem, k), k
+    for k in MAP_NAMES + ("dmap", "dcmap", "icc", "icmat", "outc", "icczero"):
+        a, b = getattr(from_files, k), getattr(in_mem, k)
+        assert a.dtype == b.dtype and a.shape == b.shape, k
+        assert a.tobytes() == b.tobytes(), k
+    assert 0 < from_files.ncoordszero <= 5 and from_files.ncoordsout == 9
+
+
+def test_device_id_forms_match_reference_launcher():
+    assert launcher.parse_cuda_device_id(None) == "0"
+    assert launcher.parse_cuda_device_id(2) == "2"
+    assert launcher.parse_cuda_device_id("3") == "3"
+    assert launcher.parse_cuda_device_id([0, 1, 2]) == "0,1,2"
+    assert launcher.device_ids_of([1, 3]) == (1, 3)
+    for bad in (-1, "a", [0, -1], 1.5, "0,1"):
+        with pytest.raises(ValueError):
+            launcher.parse_cuda_device_id(bad)
+    if HAVE_REF:
+        from fullwave.solver.launcher import Launcher as RefLauncher
+        for v in (None, 2, "3", [0, 1, 2]):
+            assert RefLauncher._parse_cuda_device_id(v) == launcher.parse_cuda_device_id(v)
+
+
+@needs_ref
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(40, 48), (20, 24, 28)])
+def test_solver_run_identical_through_every_boundary(built_lib, shape):
+    from fullwave25_b200 import build
+    fw, grid, medium, source, sensor = ref_objects.build(shape, n_steps=60, n_sensors=12, n_air=6, modT=3)
+    kw = dict(pml_layer_thickness_px=6, n_transition_layer=4)
+    ndim = len(shape)
+    out = {}
+    with tempfile.TemporaryDirectory() as td:
+        s_ref = fw.Solver(Path(td) / "ref", grid, medium, source, sensor,
+                          path_fullwave_simulation_bin=ref_objects.ref_bin(ndim), **kw)
+        out["reference binary"] = s_ref.run()
+        s_cli = fw.Solver(Path(td) / "cli", grid, medium, source, sensor,
+                          path_fullwave_simulation_bin=build.CLI, **kw)
+        out["fw25_engine executable"] = s_cli.run()
+        undo = launcher.install()
+        try:
+            s_ins = fw.Solver(Path(td) / "ins", grid, medium, source, sensor,
+                              path_fullwave_simulation_bin=build.CLI, **kw)
+            assert isinstance(s_ins.fullwave_launcher, launcher.Launcher)
+            out["launcher.install()"] = s_ins.run()
+        finally:
+            undo()
+        out["run_solver (no disk)"] = launcher.run_solver(s_ref)
+    want = out.pop("reference binary")
+    assert want.shape == (12, 20) and np.abs(want).max() > 0
+    for name, got in out.items():
+        assert got.shape == want.shape, name
+        np.testing.assert_array_equal(got, want, err_msg=name)
