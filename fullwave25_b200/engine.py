@@ -171,8 +171,8 @@ class Engine:
             self.set_variant(variant)
 
     def close(self) -> None:
-        if getattr(self, "_h", None):
-            lib().fw25_destroy(self._h)
+        if getattr(self, "_h", None) and _lib is not None:   # (_lib is None during interpreter shutdown)
+            _lib.fw25_destroy(self._h)
             self._h = None
 
     __del__ = close

@@ -87,6 +87,7 @@ def gather_frames(drv: SlabDriver, eng: SlabEngine, n_frames: int, ncoordsout: i
     that order whatever the GPU count); other ranks return None."""
     import torch
     drv.finish()
+    torch.cuda.synchronize(eng.device)     # the sweeps ran on torch streams, not on the engine's own stream
     eng.eng.sync()
     local = eng.eng.read_frames(0, n_frames) if n_frames else np.zeros((0, eng.eng.n_local_sensors), np.float32)
     ids = eng.eng.local_sensor_ids()

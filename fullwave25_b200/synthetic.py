@@ -143,7 +143,8 @@ def make_problem(shape, *, nT: int, f0: float = 1e6, c0: float = 1540.0, ppw: in
     for layer in range(source_layers):  # delay each layer by one cell's travel time (as examples/wave_3d does)
         sel = icc[:, 0] == nb + layer
         shift = int(round(layer * dx / c0 / dt))
-        icmat[sel, shift:] = pulse[: nTic - shift]
+        if shift < nTic:
+            icmat[sel, shift:] = pulse[: nTic - shift]
 
     # point sensors + air voxels scattered in the user domain (row-major order like np.where)
     user = np.zeros(shape, bool)

@@ -127,7 +127,8 @@ def make_slab(global_shape, gx0: int, gx1: int, *, device, nT: int, f0: float = 
     rows = np.zeros((source_layers, nTic), np.float32)
     for l in range(source_layers):
         shift = int(round(l * dx / c0 / dt))
-        rows[l, shift:] = pulse[: nTic - shift]
+        if shift < nTic:
+            rows[l, shift:] = pulse[: nTic - shift]
     icmat = np.repeat(rows, yy.size, axis=0)
     rng = np.random.default_rng(seed)
 

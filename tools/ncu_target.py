@@ -1,0 +1,20 @@
+"""Short run of the tiled sweeps on a device-generated medium, for ncu captures (profiles/)."""
+import sys
+from pathlib import Path
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import torch
+from fullwave25_b200 import synthetic_device
+from fullwave25_b200.runtime import SlabEngine
+from fullwave25_b200.slab import partition
+
+shape = tuple(int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else "256x620x620").split("x"))
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+dev = torch.device("cuda", 0)
+slab = partition(shape[0], 1)[0]
+pb, maps = synthetic_device.make_slab(shape, 0, shape[0], device=dev, nT=steps, n_pml=36, n_trans=36, block=24)
+dm = {k: (v if k == "pitch" else v.data_ptr()) for k, v in maps.items()}
+eng = SlabEngine(pb, slab, dev, device_maps=dm)
+eng.eng.step(steps)
+eng.eng.sync()
+print("done", eng.eng.launches, "launches")

@@ -1,0 +1,49 @@
+"""Run under torchrun on N GPUs: x-slab run of a seeded case through SlabEngine + NCCL halo exchange; rank 0
+compares the assembled sensor frames with the single-domain oracle (bit-exact) and prints a JSON verdict.
+
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 tools/slab_check.py het3d
+"""
+import json
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+import torch
+import torch.distributed as dist
+
+from fullwave25_b200.runtime import SlabEngine, TorchComm, gather_frames
+from fullwave25_b200.slab import SlabDriver, partition
+from tests.test_slab import _problem
+
+
+def main():
+    case = sys.argv[1] if len(sys.argv) > 1 else "het3d"
+    rank, world, local = (int(os.environ[k]) for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    pb = _problem(case)
+    slab = partition(pb.nX, world)[rank]
+    sub = pb.slab(slab.gx0, slab.gx1).normalise()
+    eng = SlabEngine(sub, slab, dev)
+    main_s, bnd = torch.cuda.Stream(dev), torch.cuda.Stream(dev, priority=-1)
+    drv = SlabDriver(slab, eng, TorchComm(dist), pb.modT, streams=(main_s, bnd), ndim=pb.ndim)
+    for _ in range(pb.nT):
+        drv.step()
+    got = gather_frames(drv, eng, pb.n_frames, pb.ncoordsout, dist)
+    if rank == 0:
+        from oracle import oracle
+        want = oracle.run(pb)
+        print("SLABCHECK " + json.dumps({"case": case, "world": world, "bit_exact": bool(np.array_equal(got, want)),
+                                         "absmax": float(np.abs(want).max()), "n_diff": int((got != want).sum())}), flush=True)
+    eng.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
