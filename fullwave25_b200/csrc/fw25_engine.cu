@@ -71,10 +71,12 @@ struct Engine {
   int variant = 0;
   int64_t h2d_bytes = 0;
   TiledPlan *plan = nullptr;   // TMA-tiled sweeps (3D)
+  WsPlan *ws = nullptr;        // warp-specialised all-TMA sweeps (3D)
 
   ~Engine() {
     cudaSetDevice(device);
     tiled_plan_destroy(plan);
+    ws_plan_destroy(ws);
     for (void *p : owned) cudaFree(p);
     if (stream) cudaStreamDestroy(stream);
   }
@@ -204,6 +206,10 @@ struct Engine {
       memcpy(hd.data(), pb.dmap, hd.size() * 4);
       plan = tiled_plan_create(F, G, hd.data(), stream, &perr);
       if (!plan) fail(2, "tiled sweep setup failed: " + perr);
+      if (ws_supported(ndim, G)) {
+        ws = ws_plan_create(F, G, hd.data(), stream, &perr);
+        if (!ws) fail(2, "warp-specialised sweep setup failed: " + perr);
+      }
     }
 
     // ---- coordinate lists -> linear indices (bit-exact integer maps)
@@ -281,6 +287,7 @@ struct Engine {
     FW_CUDA(cudaStreamSynchronize(stream));
   }
 
+  bool use_ws() const { return ws != nullptr && (variant == 0 || variant == 3); }
   bool use_tiled() const { return plan != nullptr && variant != 1; }
 
   void clamp(int gx_lo, int gx_hi, int &a_lo, int &a_hi) const {
@@ -297,6 +304,7 @@ struct Engine {
     int a_lo, a_hi;
     clamp(gx_lo, gx_hi, a_lo, a_hi);
     if (a_hi <= a_lo) return;
+    if (use_ws()) { launches += launch_sweep_u_ws(ws, F, G, a_lo, a_hi, st); return; }
     if (use_tiled()) { launches += launch_sweep_u_tiled(plan, F, G, a_lo, a_hi, st); return; }
     launch_sweep_u_simple(ndim, F, G, a_lo, a_hi, st);
     launches += (a_hi - a_lo + 32767) / 32768;
@@ -305,6 +313,7 @@ struct Engine {
     int a_lo, a_hi;
     clamp(gx_lo, gx_hi, a_lo, a_hi);
     if (a_hi <= a_lo) return;
+    if (use_ws()) { launches += launch_sweep_p_ws(ws, F, G, a_lo, a_hi, st); return; }
     if (use_tiled()) { launches += launch_sweep_p_tiled(plan, F, G, a_lo, a_hi, st); return; }
     launch_sweep_p_simple(ndim, F, G, a_lo, a_hi, st);
     launches += (a_hi - a_lo + 32767) / 32768;
@@ -473,8 +482,9 @@ void *fw25_field_ptr(fw25_engine *h, const char *name) { return h->e.field(name)
 int32_t fw25_current_step(const fw25_engine *h) { return h->e.t; }
 int64_t fw25_launch_count(const fw25_engine *h) { return h->e.launches; }
 int fw25_set_kernel_variant(fw25_engine *h, int32_t v) {
-  if (v < 0 || v > 2) { g_err = "fw25_set_kernel_variant: variant must be 0, 1 or 2"; return 1; }
+  if (v < 0 || v > 3) { g_err = "fw25_set_kernel_variant: variant must be 0..3"; return 1; }
   if (v == 2 && !h->e.plan) { g_err = "fw25_set_kernel_variant: the TMA-tiled sweeps need a 3D problem"; return 1; }
+  if (v == 3 && !h->e.ws) { g_err = "fw25_set_kernel_variant: the warp-specialised sweeps need a 3D problem with < 2^32 cells per array"; return 1; }
   h->e.variant = v;
   return 0;
 }

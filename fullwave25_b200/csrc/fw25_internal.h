@@ -18,6 +18,14 @@ void tiled_plan_destroy(TiledPlan *pl);
 int launch_sweep_u_tiled(const TiledPlan *pl, const Fields &F, const Geom &G, int a_lo, int a_hi, cudaStream_t st);
 int launch_sweep_p_tiled(const TiledPlan *pl, const Fields &F, const Geom &G, int a_lo, int a_hi, cudaStream_t st);
 
+// warp-specialised all-TMA sweeps (3D): fw25_sweeps_ws.cu
+struct WsPlan;
+bool ws_supported(int ndim, const Geom &G);
+WsPlan *ws_plan_create(const Fields &F, const Geom &G, const float *host_dmap, cudaStream_t st, std::string *err);
+void ws_plan_destroy(WsPlan *pl);
+int launch_sweep_u_ws(const WsPlan *pl, const Fields &F, const Geom &G, int a_lo, int a_hi, cudaStream_t st);
+int launch_sweep_p_ws(const WsPlan *pl, const Fields &F, const Geom &G, int a_lo, int a_hi, cudaStream_t st);
+
 // point kernels: fw25_points.cu
 void launch_dcmap_mask(int32_t *dcmap, long long cells, int pitch, int nC, int nB, long long first_plane,
                        long long limit, cudaStream_t st);

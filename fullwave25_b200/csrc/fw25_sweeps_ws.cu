@@ -1,0 +1,515 @@
+// fw25_sweeps_ws.cu -- 3D sweeps for sm_100a, warp-specialised: every global READ goes through TMA.
+//
+// Same 2.5-D scheme as fw25_sweeps_tiled.cu (march along x over (y,z) tiles of TY x 32 cells, x column of the
+// stencil field in registers), but:
+//   * a dedicated PRODUCER warp (one elected lane) issues all loads as cp.async.bulk.tensor.3d: the haloed
+//     stencil tiles into a 4-slot ring AND the 16/18 point-wise arrays of the plane (centre tiles TY x 32) into
+//     a 2-stage buffer, one plane ahead, completion on "full" mbarriers;
+//   * TY CONSUMER warps (one per tile row, a warp = 32 contiguous z = one 128-byte line) read everything with
+//     LDS at compile-time offsets, do the arithmetic, write the 9 (7) results with streaming stores, and hand
+//     the buffers back through "empty" mbarriers (one arrival per warp).  No __syncthreads in the loop, no
+//     long-scoreboard waits on global loads, no per-array address arithmetic for loads, no staging registers.
+//
+// Arithmetic: operation for operation the reference's (fw25_kernels.cuh); bit-identical to the other variants.
+// Replaces fd_u / fd_p (3D PTX L38-675 / L677-1323).
+#include <cuda.h>
+
+#include <cstddef>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "fw25_internal.h"
+#include "fw25_kernels.cuh"
+#include "fw25_tma.cuh"
+
+#ifndef FW25_WS_TY
+#define FW25_WS_TY 8      // tile rows = consumer warps per CTA
+#endif
+#ifndef FW25_WS_MINB
+#define FW25_WS_MINB 3    // resident CTAs per SM the register budget is sized for
+#endif
+
+namespace fw25 {
+
+namespace {
+
+constexpr int TZ = 32;
+constexpr int NH = 4;   // halo-tile ring slots: planes x, x+1 in use, two in flight
+constexpr int NP = 2;   // point-wise stages: plane x in use, x+1 in flight
+
+struct StencilTab {
+  float4 d03, d47, e;
+};
+
+// tensor-map slots in the plan's device array
+enum : int {
+  // fd_u
+  MU_PHALO = 0, MU_PNEW, MU_DC, MU_RHO, MU_K, MU_KX, MU_A1, MU_B1, MU_A2, MU_B2, MU_Q0, MU_Q1, MU_Q2,
+  MU_M00, MU_M01, MU_M10, MU_M11, MU_M20, MU_M21, MU_END,
+  // fd_p
+  MP_UHALO = MU_END, MP_VHALO, MP_WHALO, MP_UNEW, MP_DC, MP_K, MP_BETA, MP_KU, MP_A1, MP_B1, MP_A2, MP_B2, MP_P,
+  MP_F00, MP_F01, MP_F10, MP_F11, MP_F20, MP_F21, MP_END,
+};
+constexpr int NPW_U = MU_END - MU_PNEW;   // 18 point-wise tiles per plane in fd_u
+constexpr int NPW_P = MP_END - MP_UNEW;   // 16 in fd_p
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+
+template <int TY>
+struct alignas(128) SmemU {
+  float halo[NH][TY + 2 * M][TZ + 2 * M];
+  float pw[NP][NPW_U][TY][TZ];
+  uint64_t full_h[NH], empty_h[NH], full_p[NP], empty_p[NP];
+};
+
+template <int TY>
+struct alignas(128) SmemP {
+  struct alignas(128) Halo {
+    alignas(128) float u[TY + 2][TZ + 8];
+    alignas(128) float v[TY + 2 * M][TZ + 8];
+    alignas(128) float w[TY + 2][TZ + 2 * M];
+  } halo[NH];
+  float pw[NP][NPW_P][TY][TZ];
+  uint64_t full_h[NH], empty_h[NH], full_p[NP], empty_p[NP];
+};
+
+// ------------------------------------------------------------------------------------------ fd_u
+template <int TY, int MINB>
+__global__ void __launch_bounds__((TY + 1) * TZ, MINB)
+    k_sweep_u_ws(const CUtensorMap *__restrict__ maps, const Fields F, const Geom G,
+                 const StencilTab *__restrict__ tab, int a_lo, int a_hi, int Lx) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  SmemU<TY> &S = *reinterpret_cast<SmemU<TY> *>(smem_raw);
+  constexpr int HY = TY + 2 * M, HZ = TZ + 2 * M;
+  constexpr uint32_t HALO_BYTES = HY * HZ * 4, PW_BYTES = NPW_U * TY * TZ * 4;
+
+  const int tz = threadIdx.x, ty = threadIdx.y;
+  const int z0 = blockIdx.x * TZ, y0 = M + blockIdx.y * TY;
+  const int xa = a_lo + blockIdx.z * Lx;
+  const int xb = min(xa + Lx, a_hi);
+
+  if (ty == TY && tz == 0) {
+#pragma unroll
+    for (int s = 0; s < NH; ++s) { mbar_init(&S.full_h[s], 1); mbar_init(&S.empty_h[s], TY); }
+#pragma unroll
+    for (int s = 0; s < NP; ++s) { mbar_init(&S.full_p[s], 1); mbar_init(&S.empty_p[s], TY); }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (ty == TY) {
+    // ---------------- producer warp: one lane issues every load of the chunk
+    if (tz == 0) {
+      for (int P = xa; P <= xb; ++P) {
+        const int n = P - xa;          // ring slots are indexed relative to the chunk start
+        {
+          const int s = n & (NH - 1), k = n / NH;
+          if (k > 0) mbar_wait(&S.empty_h[s], (k - 1) & 1);
+          mbar_arrive_expect_tx(&S.full_h[s], HALO_BYTES);
+          tma_load_3d(&S.halo[s][0][0], &maps[MU_PHALO], z0 - M, y0 - M, P, &S.full_h[s]);
+        }
+        if (P < xb) {
+          const int s = n & (NP - 1), k = n / NP;
+          if (k > 0) mbar_wait(&S.empty_p[s], (k - 1) & 1);
+          mbar_arrive_expect_tx(&S.full_p[s], PW_BYTES);
+          tma_load_3d(&S.pw[s][0][0][0], &maps[MU_PNEW], z0, y0, P + M, &S.full_p[s]);   // p[x+8]
+#pragma unroll
+          for (int a = 1; a < NPW_U; ++a)
+            tma_load_3d(&S.pw[s][a][0][0], &maps[MU_PNEW + a], z0, y0, P, &S.full_p[s]);
+        }
+      }
+    }
+    return;
+  }
+
+  // ---------------- consumer warps
+  const int z = z0 + tz, y = y0 + ty;
+  const bool act = (z >= M) && (z < G.nC - M) && (y < G.nB - M);
+  const int sy = ty + M, sz = tz + M;
+  const unsigned sA = (unsigned)G.sA, sB = (unsigned)G.sB;
+  unsigned gi = (unsigned)xa * sA + (unsigned)y * sB + (unsigned)z;   // element index (< 2^32, checked on the host)
+  const float *__restrict__ p = F.p;
+
+  float pc[16];
+  float pm_y1 = 0.f, pm_z1 = 0.f;
+  if (act) {
+#pragma unroll
+    for (int j = 0; j < 15; ++j) pc[j] = p[gi + (unsigned)(j - 7) * sA];
+    pm_y1 = p[gi - sA + sB];
+    pm_z1 = p[gi - sA + 1];
+  } else {
+#pragma unroll
+    for (int j = 0; j < 15; ++j) pc[j] = 0.f;
+  }
+  pc[15] = 0.f;
+
+  mbar_wait(&S.full_h[0], 0);
+  const int len = xb - xa;
+
+#pragma unroll 4
+  for (int n = 0; n < len; ++n, gi += sA) {
+    mbar_wait(&S.full_h[(n + 1) & (NH - 1)], ((n + 1) / NH) & 1);
+    mbar_wait(&S.full_p[n & (NP - 1)], (n / NP) & 1);
+
+    if (act) {
+      const float(*c0)[HZ] = S.halo[n & (NH - 1)];
+      const float(*c1)[HZ] = S.halo[(n + 1) & (NH - 1)];
+      const float(*W)[TY][TZ] = S.pw[n & (NP - 1)];
+      pc[15] = W[0][ty][tz];
+      const int ci = __float_as_int(W[MU_DC - MU_PNEW][ty][tz]);
+      const StencilTab T = tab[ci];
+      const float D[9] = {0.f, T.d03.x, T.d03.y, T.d03.z, T.d03.w, T.d47.x, T.d47.y, T.d47.z, T.d47.w};
+      const float E = T.e.x;
+      const float pcen = pc[7];
+
+      float yv[16], zv[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        yv[j] = (j == 7) ? pcen : c0[sy + j - 7][sz];
+        zv[j] = (j == 7) ? pcen : c0[sy][sz + j - 7];
+      }
+      float gA = 0.f, gB = 0.f, gC = 0.f;
+#pragma unroll
+      for (int k = 1; k <= M; ++k) {
+        gA = fma_(D[k], sub_(pc[7 + k], pc[8 - k]), gA);
+        gB = fma_(D[k], sub_(yv[7 + k], yv[8 - k]), gB);
+        gC = fma_(D[k], sub_(zv[7 + k], zv[8 - k]), gC);
+      }
+      const float p110 = c1[sy + 1][sz], p1m0 = c1[sy - 1][sz], p101 = c1[sy][sz + 1], p10m = c1[sy][sz - 1];
+      const float p011 = c0[sy + 1][sz + 1], p01m = c0[sy + 1][sz - 1], p0m1 = c0[sy - 1][sz + 1];
+      const float p100 = pc[8], pm00 = pc[6];
+      const float p010 = yv[8], p0m0 = yv[6], p001 = zv[8], p00m = zv[6];
+      float cA = sub_(p110, p010);
+      cA = add_(cA, p1m0); cA = sub_(cA, p0m0);
+      cA = add_(cA, p101); cA = sub_(cA, p001);
+      cA = add_(cA, p10m); cA = sub_(cA, p00m);
+      float cB = sub_(p110, p100);
+      cB = add_(cB, pm_y1); cB = sub_(cB, pm00);
+      cB = add_(cB, p011); cB = sub_(cB, p001);
+      cB = add_(cB, p01m); cB = sub_(cB, p00m);
+      float cC = sub_(p101, p100);
+      cC = add_(cC, pm_z1); cC = sub_(cC, pm00);
+      cC = add_(cC, p011); cC = sub_(cC, p010);
+      cC = add_(cC, p0m1); cC = sub_(cC, p0m0);
+      pm_y1 = p010; pm_z1 = p001;
+
+      const float dX = G.dX;
+      gA = div_(fma_(E, cA, gA), dX);
+      gB = div_(fma_(E, cB, gB), dX);
+      gC = div_(fma_(E, cC, gC), dX);
+
+      const float rho = W[MU_RHO - MU_PNEW][ty][tz], Kc = W[MU_K - MU_PNEW][ty][tz], kx = W[MU_KX - MU_PNEW][ty][tz];
+      const float a1 = W[MU_A1 - MU_PNEW][ty][tz], b1 = W[MU_B1 - MU_PNEW][ty][tz];
+      const float a2 = W[MU_A2 - MU_PNEW][ty][tz], b2 = W[MU_B2 - MU_PNEW][ty][tz];
+      const float s = div_(div_(G.dT, rho), fma_(rcp_(Kc), pcen, 1.0f));
+      const float m00 = fma_(b1, W[MU_M00 - MU_PNEW][ty][tz], mul_(gA, a1));
+      const float m01 = fma_(b2, W[MU_M01 - MU_PNEW][ty][tz], mul_(gA, a2));
+      const float m10 = fma_(b1, W[MU_M10 - MU_PNEW][ty][tz], mul_(gB, a1));
+      const float m11 = fma_(b2, W[MU_M11 - MU_PNEW][ty][tz], mul_(gB, a2));
+      const float m20 = fma_(b1, W[MU_M20 - MU_PNEW][ty][tz], mul_(gC, a1));
+      const float m21 = fma_(b2, W[MU_M21 - MU_PNEW][ty][tz], mul_(gC, a2));
+      const float q0 = fma_(-s, add_(add_(div_(gA, kx), m00), m01), W[MU_Q0 - MU_PNEW][ty][tz]);
+      const float q1 = fma_(-s, add_(add_(div_(gB, kx), m10), m11), W[MU_Q1 - MU_PNEW][ty][tz]);
+      const float q2 = fma_(-s, add_(add_(div_(gC, kx), m20), m21), W[MU_Q2 - MU_PNEW][ty][tz]);
+      __stcs(F.psi[0][0] + gi, m00); __stcs(F.psi[0][1] + gi, m01);
+      __stcs(F.psi[1][0] + gi, m10); __stcs(F.psi[1][1] + gi, m11);
+      __stcs(F.psi[2][0] + gi, m20); __stcs(F.psi[2][1] + gi, m21);
+      __stcs(F.q[0] + gi, q0); __stcs(F.q[1] + gi, q1); __stcs(F.q[2] + gi, q2);
+#pragma unroll
+      for (int j = 0; j < 15; ++j) pc[j] = pc[j + 1];
+    }
+    __syncwarp();
+    if (tz == 0) {
+      mbar_arrive(&S.empty_h[n & (NH - 1)]);
+      mbar_arrive(&S.empty_p[n & (NP - 1)]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ fd_p
+template <int TY, int MINB>
+__global__ void __launch_bounds__((TY + 1) * TZ, MINB)
+    k_sweep_p_ws(const CUtensorMap *__restrict__ maps, const Fields F, const Geom G,
+                 const StencilTab *__restrict__ tab, int a_lo, int a_hi, int Lx) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  SmemP<TY> &S = *reinterpret_cast<SmemP<TY> *>(smem_raw);
+  constexpr uint32_t U_BYTES = (TY + 2) * (TZ + 8) * 4, V_BYTES = (TY + 2 * M) * (TZ + 8) * 4,
+                     W_BYTES = (TY + 2) * (TZ + 2 * M) * 4, PW_BYTES = NPW_P * TY * TZ * 4;
+
+  const int tz = threadIdx.x, ty = threadIdx.y;
+  const int z0 = blockIdx.x * TZ, y0 = M + blockIdx.y * TY;
+  const int xa = a_lo + blockIdx.z * Lx;
+  const int xb = min(xa + Lx, a_hi);
+  const int len = xb - xa;
+
+  if (ty == TY && tz == 0) {
+#pragma unroll
+    for (int s = 0; s < NH; ++s) { mbar_init(&S.full_h[s], 1); mbar_init(&S.empty_h[s], TY); }
+#pragma unroll
+    for (int s = 0; s < NP; ++s) { mbar_init(&S.full_p[s], 1); mbar_init(&S.empty_p[s], TY); }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (ty == TY) {
+    // producer: halo tiles of planes xa-1 .. xb (ring index m = plane - (xa-1)), point-wise tiles of xa .. xb-1
+    if (tz == 0) {
+      for (int m = 0; m <= len + 1; ++m) {
+        {
+          const int P = xa - 1 + m, s = m & (NH - 1), k = m / NH;
+          if (k > 0) mbar_wait(&S.empty_h[s], (k - 1) & 1);
+          mbar_arrive_expect_tx(&S.full_h[s], U_BYTES + V_BYTES + W_BYTES);
+          tma_load_3d(&S.halo[s].u[0][0], &maps[MP_UHALO], z0 - 4, y0 - 1, P, &S.full_h[s]);
+          tma_load_3d(&S.halo[s].v[0][0], &maps[MP_VHALO], z0 - 4, y0 - M, P, &S.full_h[s]);
+          tma_load_3d(&S.halo[s].w[0][0], &maps[MP_WHALO], z0 - M, y0 - 1, P, &S.full_h[s]);
+        }
+        const int n = m - 1;           // point-wise plane xa + n goes out right after halo plane xa + n
+        if (n >= 0 && n < len) {
+          const int P = xa + n, s = n & (NP - 1), k = n / NP;
+          if (k > 0) mbar_wait(&S.empty_p[s], (k - 1) & 1);
+          mbar_arrive_expect_tx(&S.full_p[s], PW_BYTES);
+          tma_load_3d(&S.pw[s][0][0][0], &maps[MP_UNEW], z0, y0, P + M - 1, &S.full_p[s]);   // u[x+7]
+#pragma unroll
+          for (int a = 1; a < NPW_P; ++a)
+            tma_load_3d(&S.pw[s][a][0][0], &maps[MP_UNEW + a], z0, y0, P, &S.full_p[s]);
+        }
+      }
+    }
+    return;
+  }
+
+  const int z = z0 + tz, y = y0 + ty;
+  const bool act = (z >= M) && (z < G.nC - M) && (y < G.nB - M);
+  const unsigned sA = (unsigned)G.sA, sB = (unsigned)G.sB;
+  unsigned gi = (unsigned)xa * sA + (unsigned)y * sB + (unsigned)z;
+  const float *__restrict__ u = F.q[0];
+
+  float uc[16];   // uc[j] = u[x - 8 + j]
+  if (act) {
+#pragma unroll
+    for (int j = 0; j < 15; ++j) uc[j] = u[gi + (unsigned)(j - 8) * sA];
+  } else {
+#pragma unroll
+    for (int j = 0; j < 15; ++j) uc[j] = 0.f;
+  }
+  uc[15] = 0.f;
+
+  mbar_wait(&S.full_h[0], 0);
+  mbar_wait(&S.full_h[1], 0);
+
+#pragma unroll 4
+  for (int n = 0; n < len; ++n, gi += sA) {
+    // ring index of plane x-1 is n, of x is n+1, of x+1 is n+2
+    mbar_wait(&S.full_h[(n + 2) & (NH - 1)], ((n + 2) / NH) & 1);
+    mbar_wait(&S.full_p[n & (NP - 1)], (n / NP) & 1);
+
+    if (act) {
+      const typename SmemP<TY>::Halo &Sm = S.halo[n & (NH - 1)];
+      const typename SmemP<TY>::Halo &S0 = S.halo[(n + 1) & (NH - 1)];
+      const typename SmemP<TY>::Halo &S1 = S.halo[(n + 2) & (NH - 1)];
+      const float(*W)[TY][TZ] = S.pw[n & (NP - 1)];
+      uc[15] = W[0][ty][tz];
+      const int ci = __float_as_int(W[MP_DC - MP_UNEW][ty][tz]);
+      const StencilTab T = tab[ci];
+      const float D[9] = {0.f, T.d03.x, T.d03.y, T.d03.z, T.d03.w, T.d47.x, T.d47.y, T.d47.z, T.d47.w};
+      const float E = T.e.x;
+      const int uy = ty + 1, uz = tz + 4;
+      const int vy = ty + M, vz = tz + 4;
+      const int wy = ty + 1, wz = tz + M;
+
+      float hA = 0.f, hB = 0.f, hC = 0.f;
+#pragma unroll
+      for (int k = 1; k <= M; ++k) {   // PTX L799-966: ascending k
+        hA = fma_(D[k], sub_(uc[7 + k], uc[8 - k]), hA);
+        hB = fma_(D[k], sub_(S0.v[vy + k - 1][vz], S0.v[vy - k][vz]), hB);
+        hC = fma_(D[k], sub_(S0.w[wy][wz + k - 1], S0.w[wy][wz - k]), hC);
+      }
+      float cA = sub_(S0.u[uy + 1][uz], Sm.u[uy + 1][uz]);
+      cA = add_(cA, S0.u[uy - 1][uz]); cA = sub_(cA, Sm.u[uy - 1][uz]);
+      cA = add_(cA, S0.u[uy][uz + 1]); cA = sub_(cA, Sm.u[uy][uz + 1]);
+      cA = add_(cA, S0.u[uy][uz - 1]); cA = sub_(cA, Sm.u[uy][uz - 1]);
+      float cB = sub_(S1.v[vy][vz], S1.v[vy - 1][vz]);
+      cB = add_(cB, Sm.v[vy][vz]); cB = sub_(cB, Sm.v[vy - 1][vz]);
+      cB = add_(cB, S0.v[vy][vz + 1]); cB = sub_(cB, S0.v[vy - 1][vz + 1]);
+      cB = add_(cB, S0.v[vy][vz - 1]); cB = sub_(cB, S0.v[vy - 1][vz - 1]);
+      float cC = sub_(S1.w[wy][wz], S1.w[wy][wz - 1]);
+      cC = add_(cC, Sm.w[wy][wz]); cC = sub_(cC, Sm.w[wy][wz - 1]);
+      cC = add_(cC, S0.w[wy + 1][wz]); cC = sub_(cC, S0.w[wy + 1][wz - 1]);
+      cC = add_(cC, S0.w[wy - 1][wz]); cC = sub_(cC, S0.w[wy - 1][wz - 1]);
+
+      const float dX = G.dX;
+      hA = div_(fma_(E, cA, hA), dX);
+      hB = div_(fma_(E, cB, hB), dX);
+      hC = div_(fma_(E, cC, hC), dX);
+
+      const float Kc = W[MP_K - MP_UNEW][ty][tz], bt = W[MP_BETA - MP_UNEW][ty][tz], ku = W[MP_KU - MP_UNEW][ty][tz];
+      const float a1 = W[MP_A1 - MP_UNEW][ty][tz], b1 = W[MP_B1 - MP_UNEW][ty][tz];
+      const float a2 = W[MP_A2 - MP_UNEW][ty][tz], b2 = W[MP_B2 - MP_UNEW][ty][tz];
+      const float pc = W[MP_P - MP_UNEW][ty][tz];
+      const float f00 = fma_(b1, W[MP_F00 - MP_UNEW][ty][tz], mul_(hA, a1));
+      const float f01 = fma_(b2, W[MP_F01 - MP_UNEW][ty][tz], mul_(hA, a2));
+      const float f10 = fma_(b1, W[MP_F10 - MP_UNEW][ty][tz], mul_(hB, a1));
+      const float f11 = fma_(b2, W[MP_F11 - MP_UNEW][ty][tz], mul_(hB, a2));
+      const float f20 = fma_(b1, W[MP_F20 - MP_UNEW][ty][tz], mul_(hC, a1));
+      const float f21 = fma_(b2, W[MP_F21 - MP_UNEW][ty][tz], mul_(hC, a2));
+      float Ssum = add_(div_(hA, ku), div_(hB, ku));      // PTX L1290-1305
+      Ssum = add_(div_(hC, ku), Ssum);
+      Ssum = add_(f00, Ssum); Ssum = add_(f01, Ssum); Ssum = add_(f10, Ssum); Ssum = add_(f11, Ssum);
+      Ssum = add_(f20, Ssum); Ssum = add_(f21, Ssum);
+      const float At = mul_(mul_(G.dT, Kc), Ssum);
+      const float Bt = fma_(pc, mul_(rcp_(Kc), sub_(1.0f, add_(bt, bt))), 1.0f);
+      __stcs(F.phi[0][0] + gi, f00); __stcs(F.phi[0][1] + gi, f01);
+      __stcs(F.phi[1][0] + gi, f10); __stcs(F.phi[1][1] + gi, f11);
+      __stcs(F.phi[2][0] + gi, f20); __stcs(F.phi[2][1] + gi, f21);
+      F.p[gi] = fma_(-At, Bt, pc);   // p is the next sweep's stencil field: default caching
+#pragma unroll
+      for (int j = 0; j < 15; ++j) uc[j] = uc[j + 1];
+    }
+    __syncwarp();
+    if (tz == 0) {
+      mbar_arrive(&S.empty_h[n & (NH - 1)]);     // plane x-1 is done
+      mbar_arrive(&S.empty_p[n & (NP - 1)]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host
+using EncodeFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                              const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                              CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeFn encode_fn_ws() {
+  static EncodeFn fn = [] {
+    void *sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      return reinterpret_cast<EncodeFn>(sym);
+    return (EncodeFn) nullptr;
+  }();
+  return fn;
+}
+
+bool tmap3d(CUtensorMap *m, const void *base, const Geom &G, int box_c, int box_b, std::string *err) {
+  EncodeFn fn = encode_fn_ws();
+  if (!fn) { *err = "cuTensorMapEncodeTiled is not available from this driver"; return false; }
+  const cuuint64_t dims[3] = {(cuuint64_t)G.pitch, (cuuint64_t)G.nB, (cuuint64_t)G.nA};
+  const cuuint64_t strides[2] = {(cuuint64_t)G.sB * 4, (cuuint64_t)G.sA * 4};
+  const cuuint32_t box[3] = {(cuuint32_t)box_c, (cuuint32_t)box_b, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void *>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char b[160];
+    snprintf(b, sizeof b, "cuTensorMapEncodeTiled failed with CUresult %d (pitch %d, box %dx%d)", (int)r, G.pitch,
+             box_c, box_b);
+    *err = b;
+    return false;
+  }
+  return true;
+}
+
+constexpr int TY_WS = FW25_WS_TY;
+constexpr int MINB_WS = FW25_WS_MINB;
+
+int pick_chunk_ws(const Geom &G, int planes) {
+  const long long tiles = (long long)((G.nC - M + TZ - 1) / TZ) * ((G.nB - 2 * M + TY_WS - 1) / TY_WS);
+  const long long want = 148LL * MINB_WS * 24;
+  long long chunks = (want + tiles - 1) / tiles;
+  int Lx = (int)((planes + chunks - 1) / chunks);
+  if (Lx < 16) Lx = 16;
+  if (Lx > planes) Lx = planes;
+  return Lx;
+}
+
+}  // namespace
+
+struct WsPlan {
+  CUtensorMap *maps = nullptr;   // device array [MP_END]
+  StencilTab *tab = nullptr;
+};
+
+bool ws_supported(int ndim, const Geom &G) {
+  const unsigned long long cells = (unsigned long long)G.nA * G.nB * G.pitch;
+  return ndim == 3 && G.pitch % 32 == 0 && G.nB > 2 * M && G.nC > 2 * M && cells < (1ull << 32) &&
+         encode_fn_ws() != nullptr;
+}
+
+WsPlan *ws_plan_create(const Fields &F, const Geom &G, const float *host_dmap, cudaStream_t st, std::string *err) {
+  std::vector<CUtensorMap> h(MP_END);
+  bool ok = true;
+  auto centre = [&](int slot, const void *base) { ok = ok && tmap3d(&h[slot], base, G, TZ, TY_WS, err); };
+  ok = ok && tmap3d(&h[MU_PHALO], F.p, G, TZ + 2 * M, TY_WS + 2 * M, err);
+  centre(MU_PNEW, F.p); centre(MU_DC, F.dcmap); centre(MU_RHO, F.rho); centre(MU_K, F.K); centre(MU_KX, F.kappax);
+  centre(MU_A1, F.ax1); centre(MU_B1, F.bx1); centre(MU_A2, F.ax2); centre(MU_B2, F.bx2);
+  centre(MU_Q0, F.q[0]); centre(MU_Q1, F.q[1]); centre(MU_Q2, F.q[2]);
+  centre(MU_M00, F.psi[0][0]); centre(MU_M01, F.psi[0][1]); centre(MU_M10, F.psi[1][0]);
+  centre(MU_M11, F.psi[1][1]); centre(MU_M20, F.psi[2][0]); centre(MU_M21, F.psi[2][1]);
+  ok = ok && tmap3d(&h[MP_UHALO], F.q[0], G, TZ + 8, TY_WS + 2, err) &&
+       tmap3d(&h[MP_VHALO], F.q[1], G, TZ + 8, TY_WS + 2 * M, err) &&
+       tmap3d(&h[MP_WHALO], F.q[2], G, TZ + 2 * M, TY_WS + 2, err);
+  centre(MP_UNEW, F.q[0]); centre(MP_DC, F.dcmap); centre(MP_K, F.K); centre(MP_BETA, F.beta); centre(MP_KU, F.kappau);
+  centre(MP_A1, F.au1); centre(MP_B1, F.bu1); centre(MP_A2, F.au2); centre(MP_B2, F.bu2); centre(MP_P, F.p);
+  centre(MP_F00, F.phi[0][0]); centre(MP_F01, F.phi[0][1]); centre(MP_F10, F.phi[1][0]);
+  centre(MP_F11, F.phi[1][1]); centre(MP_F20, F.phi[2][0]); centre(MP_F21, F.phi[2][1]);
+  if (!ok) return nullptr;
+
+  auto *pl = new WsPlan();
+  std::vector<StencilTab> t(G.ndmap);
+  const int nd = G.ndmap;
+  for (int c = 0; c < nd; ++c) {
+    auto Dk = [&](int k) { return host_dmap[(size_t)(2 * k) * nd + c]; };
+    t[c].d03 = make_float4(Dk(1), Dk(2), Dk(3), Dk(4));
+    t[c].d47 = make_float4(Dk(5), Dk(6), Dk(7), Dk(8));
+    t[c].e = make_float4(host_dmap[(size_t)3 * nd + c], 0.f, 0.f, 0.f);
+  }
+  cudaError_t e1 = cudaMalloc(&pl->maps, sizeof(CUtensorMap) * MP_END);
+  cudaError_t e2 = cudaMalloc(&pl->tab, sizeof(StencilTab) * nd);
+  if (e1 != cudaSuccess || e2 != cudaSuccess ||
+      cudaMemcpyAsync(pl->maps, h.data(), sizeof(CUtensorMap) * MP_END, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+      cudaMemcpyAsync(pl->tab, t.data(), sizeof(StencilTab) * nd, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+      cudaStreamSynchronize(st) != cudaSuccess ||
+      cudaFuncSetAttribute(k_sweep_u_ws<TY_WS, MINB_WS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)sizeof(SmemU<TY_WS>)) != cudaSuccess ||
+      cudaFuncSetAttribute(k_sweep_p_ws<TY_WS, MINB_WS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)sizeof(SmemP<TY_WS>)) != cudaSuccess) {
+    *err = std::string("warp-specialised plan: ") + cudaGetErrorString(cudaGetLastError());
+    if (pl->maps) cudaFree(pl->maps);
+    if (pl->tab) cudaFree(pl->tab);
+    delete pl;
+    return nullptr;
+  }
+  return pl;
+}
+
+void ws_plan_destroy(WsPlan *pl) {
+  if (!pl) return;
+  if (pl->maps) cudaFree(pl->maps);
+  if (pl->tab) cudaFree(pl->tab);
+  delete pl;
+}
+
+int launch_sweep_u_ws(const WsPlan *pl, const Fields &F, const Geom &G, int a_lo, int a_hi, cudaStream_t st) {
+  if (a_hi <= a_lo) return 0;
+  const int Lx = pick_chunk_ws(G, a_hi - a_lo);
+  dim3 blk(TZ, TY_WS + 1, 1);
+  dim3 grd((G.nC - M + TZ - 1) / TZ, (G.nB - 2 * M + TY_WS - 1) / TY_WS, (a_hi - a_lo + Lx - 1) / Lx);
+  k_sweep_u_ws<TY_WS, MINB_WS><<<grd, blk, sizeof(SmemU<TY_WS>), st>>>(pl->maps, F, G, pl->tab, a_lo, a_hi, Lx);
+  return 1;
+}
+
+int launch_sweep_p_ws(const WsPlan *pl, const Fields &F, const Geom &G, int a_lo, int a_hi, cudaStream_t st) {
+  if (a_hi <= a_lo) return 0;
+  const int Lx = pick_chunk_ws(G, a_hi - a_lo);
+  dim3 blk(TZ, TY_WS + 1, 1);
+  dim3 grd((G.nC - M + TZ - 1) / TZ, (G.nB - 2 * M + TY_WS - 1) / TY_WS, (a_hi - a_lo + Lx - 1) / Lx);
+  k_sweep_p_ws<TY_WS, MINB_WS><<<grd, blk, sizeof(SmemP<TY_WS>), st>>>(pl->maps, F, G, pl->tab, a_lo, a_hi, Lx);
+  return 1;
+}
+
+}  // namespace fw25

@@ -123,7 +123,8 @@ void *fw25_field_ptr(fw25_engine *e, const char *name);
 int32_t fw25_pitch(int32_t nZ);
 int32_t fw25_current_step(const fw25_engine *e);
 int64_t fw25_launch_count(const fw25_engine *e);
-/* select the sweep implementation: 0 = auto, 1 = simple (L1/L2-cached loads), 2 = TMA-tiled x-marching
+/* select the sweep implementation: 0 = auto (best available), 1 = simple (L1/L2-cached loads), 2 = TMA-tiled
+ * x-marching, 3 = warp-specialised all-TMA x-marching
  * (3D only; fails with an error if the variant cannot run the problem) */
 int fw25_set_kernel_variant(fw25_engine *e, int32_t variant);
 

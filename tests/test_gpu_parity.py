@@ -43,12 +43,12 @@ def test_run_matches_reference_golden_bit_exact(built_lib, name):
     np.testing.assert_array_equal(got, want)
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 3])
 @pytest.mark.parametrize("name", ["het3d", "het2d", "het3d_ragged", "het3d_long"])
 def test_final_fields_match_oracle(built_lib, name, variant):
-    """variant 1 = simple sweeps, 2 = TMA-tiled x-marching sweeps (3D only)."""
+    """variant 1 = simple sweeps, 2 = TMA-tiled x-marching, 3 = warp-specialised all-TMA (2 and 3: 3D only)."""
     pb = cases.make(name)
-    if variant == 2 and pb.ndim == 2:
+    if variant >= 2 and pb.ndim == 2:
         pytest.skip("tiled sweeps are 3D")
     _, want = oracle.run(pb, return_fields=True)
     with engine.Engine(pb, variant=variant) as e:

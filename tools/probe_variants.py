@@ -14,7 +14,7 @@ pb.dcmap_full3d = True
 print("built problem in", round(time.time() - t0, 1), "s", flush=True)
 res = {"shape": shape}
 fields = {}
-for variant in (1, 2):
+for variant in (1, 2, 3):
     with engine.Engine(pb, variant=variant) as e:
         e.step(5); e.sync()
         r = e.step_timed(steps, detail=True)
@@ -27,7 +27,7 @@ for variant in (1, 2):
                               "total_ms_per_step": r2["total_ms"] / steps, "launches": e.launches}
         fields[variant] = e.field("p")
         print(variant, res[f"v{variant}"], flush=True)
-res["variants_bit_identical"] = bool(np.array_equal(fields[1], fields[2]))
+res["variants_bit_identical"] = bool(np.array_equal(fields[1], fields[2]) and np.array_equal(fields[1], fields[3]))
 print(json.dumps(res))
 (ROOT / "gpurun_out").mkdir(exist_ok=True)
 (ROOT / "gpurun_out" / f"variants_{'x'.join(map(str, shape))}.json").write_text(json.dumps(res))
