@@ -55,8 +55,13 @@ def _stale(target: Path, deps: list[Path]) -> bool:
     return any(d.stat().st_mtime > t for d in deps)
 
 
+def _tuning_defines() -> list[str]:
+    # kernel tuning knobs (defaults live in the .cu files); e.g. FW25_WS_TY=16 FW25_WS_MINB=2 python -m ...build --force
+    return [f"-D{k}={v}" for k, v in sorted(os.environ.items()) if k.startswith("FW25_WS_") and k != "FW25_WS_WAVES"]
+
+
 def _compile(nvcc: str, src: Path, obj: Path) -> tuple[int, str]:
-    cmd = [nvcc, *NVCC_FLAGS, *_host_cxx(), "-c", "-o", str(obj), str(src)]
+    cmd = [nvcc, *NVCC_FLAGS, *_tuning_defines(), *_host_cxx(), "-c", "-o", str(obj), str(src)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     return r.returncode, " ".join(cmd) + "\n" + r.stdout + r.stderr
 

@@ -16,6 +16,7 @@
 
 #include <cstddef>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -25,11 +26,16 @@
 #include "fw25_tma.cuh"
 
 #ifndef FW25_WS_TY
-#define FW25_WS_TY 8      // tile rows = consumer warps per CTA
+#define FW25_WS_TY 16     // tile rows = consumer warps per CTA (sweep on a B200: profiles/sweep_ws_r01.txt)
 #endif
 #ifndef FW25_WS_MINB
-#define FW25_WS_MINB 3    // resident CTAs per SM the register budget is sized for
+#define FW25_WS_MINB 2    // resident CTAs per SM the register budget is sized for
 #endif
+#ifndef FW25_WS_UNROLL
+#define FW25_WS_UNROLL 4  // x steps per unrolled loop body (ring slots become compile-time offsets at 4)
+#endif
+#define FW25_PRAGMA_(x) _Pragma(#x)
+#define FW25_UNROLL_X(n) FW25_PRAGMA_(unroll n)
 
 namespace fw25 {
 
@@ -150,7 +156,7 @@ __global__ void __launch_bounds__((TY + 1) * TZ, MINB)
   mbar_wait(&S.full_h[0], 0);
   const int len = xb - xa;
 
-#pragma unroll 4
+FW25_UNROLL_X(FW25_WS_UNROLL)
   for (int n = 0; n < len; ++n, gi += sA) {
     mbar_wait(&S.full_h[(n + 1) & (NH - 1)], ((n + 1) / NH) & 1);
     mbar_wait(&S.full_p[n & (NP - 1)], (n / NP) & 1);
@@ -301,7 +307,7 @@ __global__ void __launch_bounds__((TY + 1) * TZ, MINB)
   mbar_wait(&S.full_h[0], 0);
   mbar_wait(&S.full_h[1], 0);
 
-#pragma unroll 4
+FW25_UNROLL_X(FW25_WS_UNROLL)
   for (int n = 0; n < len; ++n, gi += sA) {
     // ring index of plane x-1 is n, of x is n+1, of x+1 is n+2
     mbar_wait(&S.full_h[(n + 2) & (NH - 1)], ((n + 2) / NH) & 1);
@@ -419,7 +425,8 @@ constexpr int MINB_WS = FW25_WS_MINB;
 
 int pick_chunk_ws(const Geom &G, int planes) {
   const long long tiles = (long long)((G.nC - M + TZ - 1) / TZ) * ((G.nB - 2 * M + TY_WS - 1) / TY_WS);
-  const long long want = 148LL * MINB_WS * 24;
+  static const int waves = [] { const char *e = getenv("FW25_WS_WAVES"); return e ? atoi(e) : 24; }();
+  const long long want = 148LL * MINB_WS * waves;
   long long chunks = (want + tiles - 1) / tiles;
   int Lx = (int)((planes + chunks - 1) / chunks);
   if (Lx < 16) Lx = 16;
