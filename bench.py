@@ -207,7 +207,7 @@ def run_ours(args):
     if world == 1:
         u_ms = sum(e[0].elapsed_time(e[1]) for e in kev) / K
         p_ms = sum(e[2].elapsed_time(e[3]) for e in kev) / K
-        dom, dms, dbytes = ("fd_u (k_sweep_u_tiled)", u_ms, BYTES_FD_U) if u_ms >= p_ms else ("fd_p (k_sweep_p_tiled)", p_ms, BYTES_FD_P)
+        dom, dms, dbytes = ("fd_u (k_sweep_u_ws)", u_ms, BYTES_FD_U) if u_ms >= p_ms else ("fd_p (k_sweep_p_ws)", p_ms, BYTES_FD_P)
         ach = pts_rank * dbytes / (dms * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": None, "peak_source": peak_src, "ms_per_launch": dms,

@@ -18,7 +18,14 @@ __device__ __forceinline__ float fma_(float a, float b, float c) { return __fmaf
 __device__ __forceinline__ float mul_(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ float add_(float a, float b) { return __fadd_rn(a, b); }
 __device__ __forceinline__ float sub_(float a, float b) { return __fsub_rn(a, b); }
-__device__ __forceinline__ float div_(float a, float b) { return __fdiv_rn(a, b); }
+// IEEE-754 division, correctly rounded.  A zero numerator over a non-zero, non-NaN denominator is +-0 with the
+// xor of the signs (also for b = +-inf) -- answered directly, because div.rn's hardware range check sends
+// zero numerators down its slow path and most of a pulsed-ultrasound domain is still exactly quiet.
+__device__ __forceinline__ float div_(float a, float b) {
+  if (a == 0.0f && (b < 0.0f || b > 0.0f))
+    return __int_as_float((__float_as_int(a) ^ __float_as_int(b)) & 0x80000000);
+  return __fdiv_rn(a, b);
+}
 __device__ __forceinline__ float rcp_(float a) { return __frcp_rn(a); }
 
 // Internal layout: every field is [nA][nB][pitch] float32, C (fastest) axis padded to `pitch`

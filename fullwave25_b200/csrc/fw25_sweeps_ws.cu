@@ -87,7 +87,7 @@ struct alignas(128) SmemP {
 template <int TY, int MINB>
 __global__ void __launch_bounds__((TY + 1) * TZ, MINB)
     k_sweep_u_ws(const CUtensorMap *__restrict__ maps, const Fields F, const Geom G,
-                 const StencilTab *__restrict__ tab, int a_lo, int a_hi, int Lx) {
+                 const StencilTab *__restrict__ tab, int a_lo, int a_hi, int Lx, int hint) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SmemU<TY> &S = *reinterpret_cast<SmemU<TY> *>(smem_raw);
   constexpr int HY = TY + 2 * M, HZ = TZ + 2 * M;
@@ -97,6 +97,7 @@ __global__ void __launch_bounds__((TY + 1) * TZ, MINB)
   const int z0 = blockIdx.x * TZ, y0 = M + blockIdx.y * TY;
   const int xa = a_lo + blockIdx.z * Lx;
   const int xb = min(xa + Lx, a_hi);
+  const int len = xb - xa;
 
   if (ty == TY && tz == 0) {
 #pragma unroll
@@ -110,22 +111,31 @@ __global__ void __launch_bounds__((TY + 1) * TZ, MINB)
   if (ty == TY) {
     // ---------------- producer warp: one lane issues every load of the chunk
     if (tz == 0) {
-      for (int P = xa; P <= xb; ++P) {
-        const int n = P - xa;          // ring slots are indexed relative to the chunk start
-        {
-          const int s = n & (NH - 1), k = n / NH;
+      const uint64_t pol_stream = l2_policy_evict_first();
+      // halo tiles of planes xa .. xb (ring index m), point-wise tiles of xa .. xb-1 one plane behind them, so
+      // that waiting for a point-wise stage to drain never delays the next halo tile
+      for (int m = 0; m <= len + 1; ++m) {
+        if (m <= len) {
+          const int s = m & (NH - 1), k = m / NH;
           if (k > 0) mbar_wait(&S.empty_h[s], (k - 1) & 1);
           mbar_arrive_expect_tx(&S.full_h[s], HALO_BYTES);
-          tma_load_3d(&S.halo[s][0][0], &maps[MU_PHALO], z0 - M, y0 - M, P, &S.full_h[s]);
+          tma_load_3d(&S.halo[s][0][0], &maps[MU_PHALO], z0 - M, y0 - M, xa + m, &S.full_h[s]);
         }
-        if (P < xb) {
-          const int s = n & (NP - 1), k = n / NP;
+        const int n = m - 1;
+        if (n >= 0 && n < len) {
+          const int P = xa + n, s = n & (NP - 1), k = n / NP;
           if (k > 0) mbar_wait(&S.empty_p[s], (k - 1) & 1);
           mbar_arrive_expect_tx(&S.full_p[s], PW_BYTES);
-          tma_load_3d(&S.pw[s][0][0][0], &maps[MU_PNEW], z0, y0, P + M, &S.full_p[s]);   // p[x+8]
+          tma_load_3d(&S.pw[s][0][0][0], &maps[MU_PNEW], z0, y0, P + M, &S.full_p[s]);   // p[x+8]: stays in L2
+          if (hint) {
 #pragma unroll
-          for (int a = 1; a < NPW_U; ++a)
-            tma_load_3d(&S.pw[s][a][0][0], &maps[MU_PNEW + a], z0, y0, P, &S.full_p[s]);
+            for (int a = 1; a < NPW_U; ++a)
+              tma_load_3d_hint(&S.pw[s][a][0][0], &maps[MU_PNEW + a], z0, y0, P, &S.full_p[s], pol_stream);
+          } else {
+#pragma unroll
+            for (int a = 1; a < NPW_U; ++a)
+              tma_load_3d(&S.pw[s][a][0][0], &maps[MU_PNEW + a], z0, y0, P, &S.full_p[s]);
+          }
         }
       }
     }
@@ -154,7 +164,6 @@ __global__ void __launch_bounds__((TY + 1) * TZ, MINB)
   pc[15] = 0.f;
 
   mbar_wait(&S.full_h[0], 0);
-  const int len = xb - xa;
 
 FW25_UNROLL_X(FW25_WS_UNROLL)
   for (int n = 0; n < len; ++n, gi += sA) {
@@ -240,7 +249,7 @@ FW25_UNROLL_X(FW25_WS_UNROLL)
 template <int TY, int MINB>
 __global__ void __launch_bounds__((TY + 1) * TZ, MINB)
     k_sweep_p_ws(const CUtensorMap *__restrict__ maps, const Fields F, const Geom G,
-                 const StencilTab *__restrict__ tab, int a_lo, int a_hi, int Lx) {
+                 const StencilTab *__restrict__ tab, int a_lo, int a_hi, int Lx, int hint) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SmemP<TY> &S = *reinterpret_cast<SmemP<TY> *>(smem_raw);
   constexpr uint32_t U_BYTES = (TY + 2) * (TZ + 8) * 4, V_BYTES = (TY + 2 * M) * (TZ + 8) * 4,
@@ -264,6 +273,7 @@ __global__ void __launch_bounds__((TY + 1) * TZ, MINB)
   if (ty == TY) {
     // producer: halo tiles of planes xa-1 .. xb (ring index m = plane - (xa-1)), point-wise tiles of xa .. xb-1
     if (tz == 0) {
+      const uint64_t pol_stream = l2_policy_evict_first();
       for (int m = 0; m <= len + 1; ++m) {
         {
           const int P = xa - 1 + m, s = m & (NH - 1), k = m / NH;
@@ -278,10 +288,16 @@ __global__ void __launch_bounds__((TY + 1) * TZ, MINB)
           const int P = xa + n, s = n & (NP - 1), k = n / NP;
           if (k > 0) mbar_wait(&S.empty_p[s], (k - 1) & 1);
           mbar_arrive_expect_tx(&S.full_p[s], PW_BYTES);
-          tma_load_3d(&S.pw[s][0][0][0], &maps[MP_UNEW], z0, y0, P + M - 1, &S.full_p[s]);   // u[x+7]
+          tma_load_3d(&S.pw[s][0][0][0], &maps[MP_UNEW], z0, y0, P + M - 1, &S.full_p[s]);   // u[x+7]: stays in L2
+          if (hint) {
 #pragma unroll
-          for (int a = 1; a < NPW_P; ++a)
-            tma_load_3d(&S.pw[s][a][0][0], &maps[MP_UNEW + a], z0, y0, P, &S.full_p[s]);
+            for (int a = 1; a < NPW_P; ++a)
+              tma_load_3d_hint(&S.pw[s][a][0][0], &maps[MP_UNEW + a], z0, y0, P, &S.full_p[s], pol_stream);
+          } else {
+#pragma unroll
+            for (int a = 1; a < NPW_P; ++a)
+              tma_load_3d(&S.pw[s][a][0][0], &maps[MP_UNEW + a], z0, y0, P, &S.full_p[s]);
+          }
         }
       }
     }
@@ -423,15 +439,23 @@ bool tmap3d(CUtensorMap *m, const void *base, const Geom &G, int box_c, int box_
 constexpr int TY_WS = FW25_WS_TY;
 constexpr int MINB_WS = FW25_WS_MINB;
 
+// 1: point-wise tiles are loaded with an L2 evict-first policy.  Helps long chunks, costs ~2 % at the default
+// chunk length (profiles/sweep_lx_r01.txt), so it is off by default.
+int ws_hint() {
+  static const int h = [] { const char *e = getenv("FW25_WS_HINT"); return e ? atoi(e) : 0; }();
+  return h;
+}
+
 int pick_chunk_ws(const Geom &G, int planes) {
-  const long long tiles = (long long)((G.nC - M + TZ - 1) / TZ) * ((G.nB - 2 * M + TY_WS - 1) / TY_WS);
-  static const int waves = [] { const char *e = getenv("FW25_WS_WAVES"); return e ? atoi(e) : 24; }();
-  const long long want = 148LL * MINB_WS * waves;
-  long long chunks = (want + tiles - 1) / tiles;
-  int Lx = (int)((planes + chunks - 1) / chunks);
-  if (Lx < 16) Lx = 16;
-  if (Lx > planes) Lx = planes;
-  return Lx;
+  // Short chunks win on a B200 (profiles/sweep_lx_r01.txt: 88 % of the HBM roofline at 24-32 planes, 76 % at
+  // 262): CTAs that start together stay within a few planes of each other, so neighbouring tiles find each
+  // other's halo rows -- and the plane a column load touched seven steps earlier -- still in L2.  The
+  // prologue (15 column loads + pipeline fill) costs < 2 % at 32.
+  (void)G;
+  static const int lx_env = [] { const char *e = getenv("FW25_WS_LX"); return e ? atoi(e) : 0; }();
+  const int target = lx_env > 0 ? lx_env : 32;
+  const int chunks = (planes + target - 1) / target;
+  return (planes + chunks - 1) / chunks;
 }
 
 }  // namespace
@@ -506,7 +530,7 @@ int launch_sweep_u_ws(const WsPlan *pl, const Fields &F, const Geom &G, int a_lo
   const int Lx = pick_chunk_ws(G, a_hi - a_lo);
   dim3 blk(TZ, TY_WS + 1, 1);
   dim3 grd((G.nC - M + TZ - 1) / TZ, (G.nB - 2 * M + TY_WS - 1) / TY_WS, (a_hi - a_lo + Lx - 1) / Lx);
-  k_sweep_u_ws<TY_WS, MINB_WS><<<grd, blk, sizeof(SmemU<TY_WS>), st>>>(pl->maps, F, G, pl->tab, a_lo, a_hi, Lx);
+  k_sweep_u_ws<TY_WS, MINB_WS><<<grd, blk, sizeof(SmemU<TY_WS>), st>>>(pl->maps, F, G, pl->tab, a_lo, a_hi, Lx, ws_hint());
   return 1;
 }
 
@@ -515,7 +539,7 @@ int launch_sweep_p_ws(const WsPlan *pl, const Fields &F, const Geom &G, int a_lo
   const int Lx = pick_chunk_ws(G, a_hi - a_lo);
   dim3 blk(TZ, TY_WS + 1, 1);
   dim3 grd((G.nC - M + TZ - 1) / TZ, (G.nB - 2 * M + TY_WS - 1) / TY_WS, (a_hi - a_lo + Lx - 1) / Lx);
-  k_sweep_p_ws<TY_WS, MINB_WS><<<grd, blk, sizeof(SmemP<TY_WS>), st>>>(pl->maps, F, G, pl->tab, a_lo, a_hi, Lx);
+  k_sweep_p_ws<TY_WS, MINB_WS><<<grd, blk, sizeof(SmemP<TY_WS>), st>>>(pl->maps, F, G, pl->tab, a_lo, a_hi, Lx, ws_hint());
   return 1;
 }
 

@@ -26,17 +26,19 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
                : "memory");
 }
 
+constexpr uint32_t kSuspendHintNs = 20000;
+
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "FW25_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
       "@p bra FW25_DONE;\n"
       "bra FW25_WAIT;\n"
       "FW25_DONE:\n"
       "}\n" ::"r"(smem_addr(bar)),
-      "r"(parity)
+      "r"(parity), "r"(kSuspendHintNs)   // let the hardware park the thread instead of re-issuing the probe
       : "memory");
 }
 
@@ -48,6 +50,27 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, i
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
       ::"r"(smem_addr(dst)),
       "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_addr(bar))
+      : "memory");
+}
+
+// L2 eviction policies for TMA loads: streamed-once data should not push the stencil planes out of L2
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+
+__device__ __forceinline__ void tma_load_3d_hint(void *dst, const CUtensorMap *map, int c0, int c1, int c2,
+                                                 uint64_t *bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;"
+      ::"r"(smem_addr(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_addr(bar)), "l"(policy)
       : "memory");
 }
 

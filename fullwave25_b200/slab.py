@@ -111,9 +111,12 @@ class SlabDriver:
         return ops
 
     # one time step --------------------------------------------------------------------------------
-    def step(self):
-        """inject -> fd_u -> fd_p -> record, boundary planes first on `bnd`, exchanges overlapped with the
-        interior sweeps on `main`.  comm.record(stream) -> event, comm.wait(stream, event) order the two."""
+    def phases(self):
+        """Generator form of one step: yields the halo operations [(send, recv, peer)] at the two points
+        where planes must cross the interface, so that a caller driving SEVERAL slabs from one thread (the
+        in-process multi-GPU path) can advance all of them in lockstep.  `step()` is the one-slab-per-process
+        form.  Order per step: inject -> fd_u -> fd_p -> record, boundary planes first on `bnd`, transfers
+        overlapped with the interior sweeps on `main`."""
         s, e, c, t = self.s, self.eng, self.comm, self.t
         main, bnd = self.streams if self.streams else (None, None)
         if s.n_ranks == 1:
@@ -132,7 +135,7 @@ class SlabDriver:
             e.sweep_u(lo, hi, bnd)
         ev_bu = c.record(bnd)
         if self.exchange_enabled:
-            c.exchange(self._halo_ops(self.vel_halo), bnd)
+            yield self._halo_ops(self.vel_halo)
         ilo, ihi = self._interior_range()
         e.sweep_u(ilo, ihi, main)
         c.wait(bnd, c.record(main))          # boundary fd_p reads interior u/v/w (+ the ghosts just received)
@@ -140,7 +143,7 @@ class SlabDriver:
             e.sweep_p(lo, hi, bnd)
         ev_bp = c.record(bnd)
         if self.exchange_enabled:
-            c.exchange(self._halo_ops((("p", HALO),)), bnd)
+            yield self._halo_ops((("p", HALO),))
         self._ev_end = c.record(bnd)
         c.wait(main, ev_bu)                  # interior fd_p reads the boundary planes' u/v/w
         e.sweep_p(ilo, ihi, main)
@@ -149,8 +152,33 @@ class SlabDriver:
             e.record(t // self.modT, main)
         self.t += 1
 
+    def step(self):
+        bnd = self.streams[1] if self.streams else None
+        for ops in self.phases():
+            self.comm.exchange(ops, bnd)
+
     def finish(self):
         """Order everything still queued on the boundary stream before the caller reads results."""
         if self._ev_end is not None:
             main = self.streams[0] if self.streams else None
             self.comm.wait(main, self._ev_end)
+
+
+def step_lockstep(drivers, transfer):
+    """Advance several slabs (one SlabDriver each, all owned by this thread) by one time step.  At each halo
+    point every driver has queued its boundary work; `transfer(all_ops)` then moves the planes, where
+    all_ops[r] = [(send, recv, peer), ...] of rank r.  Used by the in-process multi-GPU runner."""
+    gens = [d.phases() for d in drivers]
+    while True:
+        batch, live = [], 0
+        for g in gens:
+            try:
+                batch.append(next(g))
+                live += 1
+            except StopIteration:
+                batch.append(None)
+        if live == 0:
+            return
+        if live != len(gens):
+            raise RuntimeError("slabs fell out of lockstep")
+        transfer(batch)
