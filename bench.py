@@ -220,7 +220,8 @@ def run_ours(args):
             try:
                 tr = json.loads(prof.read_text())
                 roof["traffic"] = tr.get("fd_u" if u_ms >= p_ms else "fd_p", {}).get("dram_bytes_per_point", 0) * pts_rank or None
-                roof["traffic_source"] = tr.get("source")
+                roof["traffic_source"] = ("dram__bytes_read.sum + dram__bytes_write.sum per point from " + str(tr.get("source"))
+                                          + ", scaled to this launch's points")
             except Exception:  # noqa: BLE001
                 pass
     else:

@@ -139,8 +139,13 @@ def marshal(pb: Problem, *, device_maps: dict | None = None, ext_state: dict | N
 
 
 def run(pb: Problem, device_ids=(0,)) -> tuple[np.ndarray, dict]:
-    """Whole job through fw25_run with HOST buffers.  Returns (genout [n_frames, ncoordsout], stats)."""
+    """Whole job with HOST buffers.  One device: fw25_run (C-ABI).  Several devices (the reference's
+    `cuda_device_id=[0, 1, ...]`): x-slabs driven from this process with peer-to-peer halo copies
+    (runtime.run_local).  Returns (genout [n_frames, ncoordsout], stats)."""
     pb.normalise()
+    if len(device_ids) > 1:
+        from . import runtime
+        return runtime.run_local(pb, list(device_ids), return_stats=True)
     s, keep = marshal(pb)
     genout = np.zeros((pb.n_frames, pb.ncoordsout), np.float32)
     ids = np.asarray(list(device_ids), np.int32)

@@ -103,3 +103,105 @@ def gather_frames(drv: SlabDriver, eng: SlabEngine, n_frames: int, ncoordsout: i
     for pid, pl in parts:
         out[:, pid] = pl
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+# In-process multi-GPU: one host thread drives one slab per device -- the reference's own model (a single
+# process looping over cudaSetDevice) and what `cuda_device_id=[0, 1, ...]` selects through the
+# launcher.  Planes move with peer-to-peer copies (torch `copy_` between devices, cudaMemcpyPeerAsync
+# underneath) queued on the SENDER's boundary stream.
+
+class _LocalOrder:
+    """Event plumbing for SlabDriver when every slab lives in this process."""
+
+    def __init__(self, torch):
+        self.torch = torch
+
+    def record(self, stream):
+        ev = self.torch.cuda.Event()
+        ev.record(stream)
+        return ev
+
+    def wait(self, stream, ev):
+        stream.wait_event(ev)
+
+    def exchange(self, ops, stream):   # never called: run_local drives the phases in lockstep
+        raise RuntimeError("use step_lockstep for in-process slabs")
+
+
+def run_local(pb, device_ids, *, variant: int = 0, return_stats: bool = False):
+    """Whole job on several GPUs of this process.  pb: host Problem (whole grid).  Returns genout
+    [n_frames, ncoordsout] in global outc order (and stats)."""
+    import time
+
+    import torch
+
+    from .slab import partition, step_lockstep
+
+    n = len(device_ids)
+    slabs = partition(pb.nX, n)
+    pb.normalise()
+    t0 = time.perf_counter()
+    engines, drivers, streams = [], [], []
+    order = _LocalOrder(torch)
+    for slab, dev_id in zip(slabs, device_ids):
+        dev = torch.device("cuda", int(dev_id))
+        with torch.cuda.device(dev):
+            sub = pb.slab(slab.gx0, slab.gx1).normalise()
+            eng = SlabEngine(sub, slab, dev, variant=variant)
+            main, bnd = torch.cuda.Stream(dev), torch.cuda.Stream(dev, priority=-1)
+        engines.append(eng)
+        streams.append((main, bnd))
+        drivers.append(SlabDriver(slab, eng, order, pb.modT, streams=(main, bnd), ndim=pb.ndim))
+    t_setup = time.perf_counter() - t0
+
+    def transfer(batch):
+        # batch[r] = [(send, recv, peer), ...]; the k-th op of r towards p pairs with the k-th op of p towards r
+        ready = []
+        for r, (main, bnd) in enumerate(streams):
+            with torch.cuda.device(engines[r].device):
+                ev = torch.cuda.Event()
+                ev.record(bnd)         # my boundary planes are final AND my ghost planes are no longer read
+            ready.append(ev)
+        recv_of = {}
+        for r, ops in enumerate(batch):
+            seen = {}
+            for _send, recv, peer in ops:
+                k = seen.get(peer, 0)
+                seen[peer] = k + 1
+                recv_of[(peer, r, k)] = recv          # what `peer` sends to `r` lands here
+        done = [[] for _ in range(n)]
+        for r, ops in enumerate(batch):
+            bnd = streams[r][1]
+            seen = {}
+            with torch.cuda.device(engines[r].device), torch.cuda.stream(bnd):
+                for send, _recv, peer in ops:
+                    k = seen.get(peer, 0)
+                    seen[peer] = k + 1
+                    bnd.wait_event(ready[peer])
+                    recv_of[(r, peer, k)].copy_(send, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(bnd)
+            for peer in seen:
+                done[peer].append(ev)
+        for r, evs in enumerate(done):
+            for ev in evs:
+                streams[r][1].wait_event(ev)
+
+    t1 = time.perf_counter()
+    for _ in range(pb.nT):
+        step_lockstep(drivers, transfer)
+    out = np.zeros((pb.n_frames, pb.ncoordsout), np.float32)
+    for drv, eng in zip(drivers, engines):
+        with torch.cuda.device(eng.device):
+            drv.finish()
+            torch.cuda.synchronize(eng.device)
+            if pb.n_frames:
+                out[:, eng.eng.local_sensor_ids()] = eng.eng.read_frames(0, pb.n_frames)
+    t_loop = time.perf_counter() - t1
+    stats = {"setup_ms": t_setup * 1e3, "loop_ms": t_loop * 1e3, "d2h_ms": 0.0,
+             "kernel_launches": sum(e.eng.launches for e in engines), "h2d_bytes": 0, "d2h_bytes": out.nbytes,
+             "point_updates": pb.n_points * pb.nT, "n_devices": n}
+    for e in engines:
+        e.close()
+    return (out, stats) if return_stats else out

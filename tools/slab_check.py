@@ -21,8 +21,21 @@ from fullwave25_b200.slab import SlabDriver, partition
 from tests.test_slab import _problem
 
 
+def local_main(case, n):
+    """Single process, n devices: engine.run(pb, device_ids=[0..n-1]) == the reference's cuda_device_id list."""
+    from fullwave25_b200 import engine
+    from oracle import oracle
+    pb = _problem(case)
+    got, stats = engine.run(pb, device_ids=tuple(range(n)))
+    want = oracle.run(pb)
+    print("SLABCHECK " + json.dumps({"case": case, "world": n, "mode": "in-process", "bit_exact": bool(np.array_equal(got, want)),
+                                     "absmax": float(np.abs(want).max()), "n_diff": int((got != want).sum())}), flush=True)
+
+
 def main():
     case = sys.argv[1] if len(sys.argv) > 1 else "het3d"
+    if "RANK" not in os.environ:
+        return local_main(case, int(sys.argv[2]) if len(sys.argv) > 2 else 2)
     rank, world, local = (int(os.environ[k]) for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
