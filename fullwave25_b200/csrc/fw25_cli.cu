@@ -6,7 +6,8 @@
 // `fullwave.Solver(..., path_fullwave_simulation_bin=<this file>)` works with zero edits upstream -- the
 // reference copies the executable into the simulation directory and runs it there (input_file_writer.py:
 // 823-827, launcher.py:196-215), which is why this binary links the engine statically instead of libfw25.so.
-// CUDA_VISIBLE_DEVICES selects the GPU like it does for the reference binary (launcher.py:206).
+// CUDA_VISIBLE_DEVICES selects the GPUs like it does for the reference binary (launcher.py:206): every visible
+// device takes one x-slab (the reference's `cuda_device_id=[0, 1, ...]`), as long as slabs stay >= 16 planes.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -103,8 +104,13 @@ int main() {
   const size_t n_frames = pb.nT > 0 ? ((size_t)pb.nT + pb.modT - 1) / pb.modT : 0;
   std::vector<float> genout(n_frames * (size_t)pb.ncoordsout);
   fw25_stats st;
-  const int32_t dev = 0;   // first device of CUDA_VISIBLE_DEVICES
-  const int rc = fw25_run(&pb, &dev, 1, genout.data(), genout.size(), &st);
+  int n_dev = fw25_device_count();
+  if (n_dev < 1) n_dev = 1;                       // fw25_run reports the CUDA error
+  while (n_dev > 1 && pb.nX / n_dev < 2 * FW25_M) --n_dev;
+  std::vector<int32_t> devs(n_dev);
+  for (int i = 0; i < n_dev; ++i) devs[i] = i;
+  printf("fw25_engine: %d GPU(s)\n", n_dev);
+  const int rc = fw25_run(&pb, devs.data(), n_dev, genout.data(), genout.size(), &st);
   if (rc != 0) {
     fprintf(stderr, "fw25_engine: error %d: %s\n", rc, fw25_last_error());
     return rc;

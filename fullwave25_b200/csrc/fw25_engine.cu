@@ -5,10 +5,14 @@
 // Differences by design: one time level (in-place leapfrog, no proceed_time copies), 64-bit indexing,
 // row-padded layout for 16-byte vector / TMA access, coordinate lists resolved to linear indices once.
 #include <algorithm>
+#include <chrono>
+#include <climits>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
+#include <unordered_set>
 #include <vector>
 
 #include "../../include/fw25.h"
@@ -61,8 +65,10 @@ struct Engine {
   long long *d_air_idx = nullptr;
   int n_air = 0;
   long long *d_sens_idx = nullptr;
-  int n_sens = 0;
+  int n_sens = 0, n_sens_global = 0;
   std::vector<int32_t> sens_ids;
+  std::vector<void *> src_owned;             // source-list allocations (replaced by reset())
+  std::unordered_set<long long> air_set;     // linear indices of the air voxels held locally
   float *d_frames = nullptr;
   int frames_cap = 0, n_frames = 0;
 
@@ -70,14 +76,31 @@ struct Engine {
   int64_t launches = 0;
   int variant = 0;
   int64_t h2d_bytes = 0;
+
+  // Whole steps replayed from a CUDA graph (small grids are launch-bound: the 2D examples step in ~10 us).  The step
+  // number then lives on the device (*d_t, advanced by the graph's last node) so that one instantiated graph
+  // serves every period.
+  int *d_t = nullptr;
+  int d_t_host = -1;             // value *d_t holds once the stream drains (-1: never set)
+  struct StepGraph {
+    cudaGraphExec_t exec = nullptr;
+    int steps = 0, nodes = 0, frames = 0;
+    bool with_inject = false, records = false;
+    int variant = -1;
+  } sg;
+  int graph_mode = -1;           // -1: auto (on for grids <= 2^27 cells), 0: off, 1: on
   TiledPlan *plan = nullptr;   // TMA-tiled sweeps (3D)
   WsPlan *ws = nullptr;        // warp-specialised all-TMA sweeps (3D)
+  Plan2D *p2d = nullptr;       // TMA-tiled sweeps (2D)
 
   ~Engine() {
     cudaSetDevice(device);
+    if (sg.exec) cudaGraphExecDestroy(sg.exec);
     tiled_plan_destroy(plan);
     ws_plan_destroy(ws);
+    plan2d_destroy(p2d);
     for (void *p : owned) cudaFree(p);
+    for (void *p : src_owned) cudaFree(p);
     if (stream) cudaStreamDestroy(stream);
   }
 
@@ -112,6 +135,74 @@ struct Engine {
                               on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream));
     if (!on_device) h2d_bytes += (int64_t)rows * G.nC * 4;
     return dst;
+  }
+
+  template <class T>
+  T *salloc(size_t n) {
+    void *p = nullptr;
+    FW_CUDA(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+    src_owned.push_back(p);
+    return static_cast<T *>(p);
+  }
+
+  bool coord_ok(const int32_t *c) const {
+    if (c[0] < 0 || c[0] >= nX_global || c[1] < 0 || c[1] >= nY) return false;
+    if (ndim == 3 && (c[2] < 0 || c[2] >= nZ)) return false;
+    return true;
+  }
+
+  // sources: every source whose plane is held locally (ghost planes included, so that the neighbour's copy
+  // of an injected cell stays consistent without an extra exchange).
+  // flag bit 0: sits in the never-updated rim; bit 1: also an air voxel (zeroing always wins, fw25_points.cu)
+  void setup_sources(int ncoords, const int32_t *icc, const float *icmat) {
+    const int nd = ndim;
+    for (void *p : src_owned) cudaFree(p);
+    src_owned.clear();
+    n_src = n_src_rim = 0;
+    std::vector<long long> idx; std::vector<int> row; std::vector<unsigned char> flag;
+    if (ncoords > 0 && (!icc || (!icmat && nTic > 0))) fail(1, "icc / icmat pointer is NULL");
+    for (int i = 0; i < ncoords; ++i) {
+      const int32_t *c = icc + (size_t)i * nd;
+      if (!coord_ok(c)) fail(1, "icc: source coordinate outside the grid");
+      if (c[0] < gx0 || c[0] >= gx0 + nXl) continue;
+      const long long li = lin(c[0], c[1], nd == 3 ? c[2] : 0);
+      idx.push_back(li);
+      row.push_back(i);
+      const bool r = is_rim(c[0], c[1], nd == 3 ? c[2] : M);
+      const bool dead = air_set.count(li) != 0;
+      flag.push_back((unsigned char)((r ? 1 : 0) | (dead ? 2 : 0)));
+      n_src_rim += (r && !dead);
+    }
+    n_src = (int)idx.size();
+    d_src_idx = salloc<long long>(n_src); d_src_row = salloc<int>(n_src); d_src_rim = salloc<unsigned char>(n_src);
+    d_icmat = nullptr;
+    if (n_src) {
+      FW_CUDA(cudaMemcpyAsync(d_src_idx, idx.data(), n_src * sizeof(long long), cudaMemcpyHostToDevice, stream));
+      FW_CUDA(cudaMemcpyAsync(d_src_row, row.data(), n_src * sizeof(int), cudaMemcpyHostToDevice, stream));
+      FW_CUDA(cudaMemcpyAsync(d_src_rim, flag.data(), n_src, cudaMemcpyHostToDevice, stream));
+      const size_t nic = (size_t)ncoords * nTic;
+      d_icmat = salloc<float>(nic);
+      if (nic) FW_CUDA(cudaMemcpyAsync(d_icmat, icmat, nic * 4, cudaMemcpyHostToDevice, stream));
+      h2d_bytes += (int64_t)nic * 4;
+    }
+    FW_CUDA(cudaStreamSynchronize(stream));  // host vectors go out of scope
+  }
+
+  // Next transmit event on the same medium: zero the wave field, t = 0, new source list.  Maps, stencil
+  // tables, tensor maps, sensors and the frame ring stay resident.
+  void reset(int nT_, int nTic_, int ncoords, const int32_t *icc, const float *icmat) {
+    if (nT_ < 0 || nTic_ < 0 || ncoords < 0) fail(1, "reset: negative count");
+    FW_CUDA(cudaStreamSynchronize(stream));
+    nT = nT_; nTic = nTic_;
+    setup_sources(ncoords, icc, icmat);
+    float *st[16] = {F.p, F.q[0], F.q[1], F.q[2], F.psi[0][0], F.psi[0][1], F.psi[1][0], F.psi[1][1], F.psi[2][0],
+                     F.psi[2][1], F.phi[0][0], F.phi[0][1], F.phi[1][0], F.phi[1][1], F.phi[2][0], F.phi[2][1]};
+    for (float *a : st)
+      if (a) FW_CUDA(cudaMemsetAsync(a, 0, cells * sizeof(float), stream));
+    t = 0;
+    d_t_host = -1;
+    n_frames = nT > 0 ? (nT + modT - 1) / modT : 0;
+    if (sg.exec) { cudaGraphExecDestroy(sg.exec); sg.exec = nullptr; }   // the graph holds the old source pointers
   }
 
   void init(const fw25_problem &pb, const fw25_slab *slab, int dev) {
@@ -212,41 +303,17 @@ struct Engine {
       }
     }
 
+    if (sweeps2d_supported(ndim, G)) {
+      std::string perr;
+      std::vector<float> hd((size_t)18 * pb.ndmap);
+      memcpy(hd.data(), pb.dmap, hd.size() * 4);
+      p2d = plan2d_create(F, G, hd.data(), stream, &perr);
+      if (!p2d) fail(2, "2D sweep setup failed: " + perr);
+    }
+
     // ---- coordinate lists -> linear indices (bit-exact integer maps)
     const int nd = ndim;
-    auto coord_ok = [&](const int32_t *c) {
-      if (c[0] < 0 || c[0] >= nX_global || c[1] < 0 || c[1] >= nY) return false;
-      if (nd == 3 && (c[2] < 0 || c[2] >= nZ)) return false;
-      return true;
-    };
-    {  // sources: every source whose plane is held locally (ghost planes included, so that the
-       // neighbour's copy of an injected cell stays consistent without an extra exchange)
-      std::vector<long long> idx; std::vector<int> row; std::vector<unsigned char> rim;
-      if (pb.ncoords > 0 && (!pb.icc || (!pb.icmat && nTic > 0))) fail(1, "icc / icmat pointer is NULL");
-      for (int i = 0; i < pb.ncoords; ++i) {
-        const int32_t *c = pb.icc + (size_t)i * nd;
-        if (!coord_ok(c)) fail(1, "icc: source coordinate outside the grid");
-        if (c[0] < gx0 || c[0] >= gx0 + nXl) continue;
-        idx.push_back(lin(c[0], c[1], nd == 3 ? c[2] : 0));
-        row.push_back(i);
-        const bool r = is_rim(c[0], c[1], nd == 3 ? c[2] : M);
-        rim.push_back(r);
-        n_src_rim += r;
-      }
-      n_src = (int)idx.size();
-      d_src_idx = dalloc<long long>(n_src); d_src_row = dalloc<int>(n_src); d_src_rim = dalloc<unsigned char>(n_src);
-      if (n_src) {
-        FW_CUDA(cudaMemcpyAsync(d_src_idx, idx.data(), n_src * sizeof(long long), cudaMemcpyHostToDevice, stream));
-        FW_CUDA(cudaMemcpyAsync(d_src_row, row.data(), n_src * sizeof(int), cudaMemcpyHostToDevice, stream));
-        FW_CUDA(cudaMemcpyAsync(d_src_rim, rim.data(), n_src, cudaMemcpyHostToDevice, stream));
-        const size_t nic = (size_t)pb.ncoords * nTic;
-        d_icmat = dalloc<float>(nic);
-        if (nic) FW_CUDA(cudaMemcpyAsync(d_icmat, pb.icmat, nic * 4, cudaMemcpyHostToDevice, stream));
-        h2d_bytes += (int64_t)nic * 4;
-      }
-      FW_CUDA(cudaStreamSynchronize(stream));  // host vectors go out of scope
-    }
-    {  // air voxels
+    {  // air voxels (ghost planes included)
       std::vector<long long> idx;
       if (pb.ncoordszero > 0 && !pb.icczero) fail(1, "icczero pointer is NULL");
       for (int i = 0; i < pb.ncoordszero; ++i) {
@@ -259,7 +326,9 @@ struct Engine {
       d_air_idx = dalloc<long long>(n_air);
       if (n_air) FW_CUDA(cudaMemcpyAsync(d_air_idx, idx.data(), n_air * sizeof(long long), cudaMemcpyHostToDevice, stream));
       FW_CUDA(cudaStreamSynchronize(stream));
+      air_set.insert(idx.begin(), idx.end());
     }
+    setup_sources(pb.ncoords, pb.icc, pb.icmat);
     {  // sensors owned by this slab, in global outc order
       std::vector<long long> idx;
       if (pb.ncoordsout > 0 && !pb.outc) fail(1, "outc pointer is NULL");
@@ -275,6 +344,7 @@ struct Engine {
       if (n_sens) FW_CUDA(cudaMemcpyAsync(d_sens_idx, idx.data(), n_sens * sizeof(long long), cudaMemcpyHostToDevice, stream));
       FW_CUDA(cudaStreamSynchronize(stream));
     }
+    n_sens_global = pb.ncoordsout;
     n_frames = nT > 0 ? (nT + modT - 1) / modT : 0;
     {
       size_t free_b = 0, total_b = 0;
@@ -284,11 +354,18 @@ struct Engine {
       frames_cap = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(n_frames, 1), budget / per));
       d_frames = dalloc<float>((size_t)frames_cap * std::max(n_sens, 1));
     }
+    d_t = dalloc<int>(1);
+    if (const char *g = getenv("FW25_GRAPH")) graph_mode = atoi(g) != 0;
+    if (const char *v = getenv("FW25_VARIANT")) {   // tuning / cross-checks: force a sweep implementation
+      const int want = atoi(v);
+      if (want == 1 || (want == 2 && (plan || p2d)) || (want == 3 && ws)) variant = want;
+    }
     FW_CUDA(cudaStreamSynchronize(stream));
   }
 
   bool use_ws() const { return ws != nullptr && (variant == 0 || variant == 3); }
   bool use_tiled() const { return plan != nullptr && variant != 1; }
+  bool use_2d() const { return p2d != nullptr && variant != 1; }
 
   void clamp(int gx_lo, int gx_hi, int &a_lo, int &a_hi) const {
     a_lo = std::max(gx_lo - gx0, G.a_rim_lo);
@@ -306,6 +383,7 @@ struct Engine {
     if (a_hi <= a_lo) return;
     if (use_ws()) { launches += launch_sweep_u_ws(ws, F, G, a_lo, a_hi, st); return; }
     if (use_tiled()) { launches += launch_sweep_u_tiled(plan, F, G, a_lo, a_hi, st); return; }
+    if (use_2d()) { launches += launch_sweep_u_2d(p2d, F, G, a_lo, a_hi, st); return; }
     launch_sweep_u_simple(ndim, F, G, a_lo, a_hi, st);
     launches += (a_hi - a_lo + 32767) / 32768;
   }
@@ -315,6 +393,7 @@ struct Engine {
     if (a_hi <= a_lo) return;
     if (use_ws()) { launches += launch_sweep_p_ws(ws, F, G, a_lo, a_hi, st); return; }
     if (use_tiled()) { launches += launch_sweep_p_tiled(plan, F, G, a_lo, a_hi, st); return; }
+    if (use_2d()) { launches += launch_sweep_p_2d(p2d, F, G, a_lo, a_hi, st); return; }
     launch_sweep_p_simple(ndim, F, G, a_lo, a_hi, st);
     launches += (a_hi - a_lo + 32767) / 32768;
   }
@@ -329,6 +408,68 @@ struct Engine {
     sweep_p(0, nX_global, stream);
     if (t % modT == 0) record(t / modT, stream);
     ++t;
+  }
+
+  bool graph_enabled() const {
+    if (graph_mode >= 0) return graph_mode != 0;
+    return cells <= ((size_t)1 << 27) && own_lo == 0 && own_hi == nX_global;
+  }
+  // Capture `steps` whole steps (inject -> fd_u -> fd_p -> record) into one graph.  Graphs that record
+  // (modT <= 32) cover whole recording periods and must start at t % modT == 0; for a long period the graph
+  // is 16 record-free steps.
+  void build_graph(bool with_inject) {
+    if (sg.exec) { cudaGraphExecDestroy(sg.exec); sg.exec = nullptr; }
+    sg.records = modT <= 32;
+    sg.steps = sg.records ? modT * std::max(1, 16 / modT) : 16;
+    sg.with_inject = with_inject;
+    sg.variant = variant;
+    sg.frames = 0;
+    const int64_t l0 = launches;
+    FW_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+    for (int j = 0; j < sg.steps; ++j) {
+      launch_inject(F.p, d_src_idx, d_src_row, d_src_rim, with_inject ? n_src : 0, d_icmat, nTic, j, d_air_idx, n_air,
+                    stream, d_t);
+      launches += ((with_inject && n_src > 0) || n_air > 0) ? 1 : 0;
+      sweep_u(0, nX_global, stream);
+      sweep_p(0, nX_global, stream);
+      if (sg.records && j % modT == 0 && n_sens > 0) {
+        launch_record_dev(F.p, d_sens_idx, n_sens, d_frames, d_t, j, modT, frames_cap, stream);
+        ++launches;
+      }
+      if (sg.records && j % modT == 0) ++sg.frames;
+    }
+    launch_tick(d_t, -1, sg.steps, stream);
+    ++launches;
+    cudaGraph_t g = nullptr;
+    FW_CUDA(cudaStreamEndCapture(stream, &g));
+    sg.nodes = (int)(launches - l0);
+    launches = l0;
+    cudaError_t e = cudaGraphInstantiate(&sg.exec, g, 0);
+    cudaGraphDestroy(g);
+    FW_CUDA(e);
+  }
+  // Advance by one step, or by a whole graph of steps when one fits: returns the number of steps taken.
+  // frame_room = frames the ring can still take before the caller must read them out.
+  int advance(int max_steps, int frame_room) {
+    if (max_steps <= 0) return 0;
+    if (graph_enabled()) {
+      const bool wi = n_src > 0 && (n_src_rim > 0 || t < nTic);
+      const bool records = modT <= 32;
+      const int steps = records ? modT * std::max(1, 16 / modT) : 16;
+      const bool phase_ok = records ? (t % modT == 0) : (t % modT != 0 && (t % modT) + steps <= modT);
+      const int frames = records ? steps / modT : 0;
+      if (phase_ok && steps <= max_steps && frames <= frame_room) {
+        if (!sg.exec || sg.with_inject != wi || sg.variant != variant) build_graph(wi);
+        if (d_t_host != t) { launch_tick(d_t, t, 0, stream); ++launches; }
+        FW_CUDA(cudaGraphLaunch(sg.exec, stream));
+        launches += sg.nodes;
+        t += sg.steps;
+        d_t_host = t;
+        return sg.steps;
+      }
+    }
+    step_once();
+    return 1;
   }
   void read_frames(int f0, int f1, float *out) {
     if (f0 < 0 || f1 < f0 || f1 - f0 > frames_cap) fail(1, "read_frames: bad frame range");
@@ -373,6 +514,330 @@ struct fw25_engine {
     return 3;                                 \
   }
 
+// ---------------------------------------------------------------------------------------------- whole job
+namespace {
+
+constexpr int M = fw25::M;
+
+int n_frames_of(const fw25_problem *pb) {
+  return pb->nT > 0 ? (pb->nT + pb->modT - 1) / std::max(pb->modT, 1) : 0;
+}
+
+// frames [f0, f1) of engine e -> columns sens_ids of genout [n_frames][ncoordsout]
+void scatter_frames(Engine &e, int f0, int f1, float *genout, int ncoordsout, std::vector<float> &tmp) {
+  if (e.n_sens == 0 || f1 <= f0) return;
+  if (e.n_sens == ncoordsout) {            // one slab owns every sensor: rows are already in global order
+    e.read_frames(f0, f1, genout + (size_t)f0 * ncoordsout);
+    return;
+  }
+  tmp.resize((size_t)(f1 - f0) * e.n_sens);
+  e.read_frames(f0, f1, tmp.data());
+  for (int f = f0; f < f1; ++f) {
+    const float *src = tmp.data() + (size_t)(f - f0) * e.n_sens;
+    float *dst = genout + (size_t)f * ncoordsout;
+    for (int i = 0; i < e.n_sens; ++i) dst[e.sens_ids[i]] = src[i];
+  }
+}
+
+// One slab per device, all driven from this host thread in lockstep -- the reference's own model (a single
+// process looping over cudaSetDevice) and what `cuda_device_id=[0, 1, ...]` /
+// CUDA_VISIBLE_DEVICES="0,1,..." select.  Same partition rule as the reference, boundary-first schedule, and
+// only the planes the stencils read cross an interface: u (8 planes), v, w (1 plane each) after fd_u, p (8) after
+// fd_p -- 18 planes per direction per step against the reference's 16 arrays x 8.  Transfers are peer-to-peer
+// copies (NVLink) queued on the sender's boundary stream and overlapped with the interior sweeps.
+struct MultiRun {
+  struct Dev {
+    fw25_engine *h = nullptr;
+    int device = 0;
+    int own_lo = 0, own_hi = 0, gx0 = 0, gx1 = 0;
+    bool has_lo = false, has_hi = false;
+    cudaStream_t bnd = nullptr;
+    cudaEvent_t ev_main = nullptr, ev_bu = nullptr, ev_bp = nullptr, ev_end = nullptr, ev_sent = nullptr;
+  };
+  std::vector<Dev> d;
+  int t = 0;
+  int64_t halo_bytes = 0;
+
+  ~MultiRun() {
+    for (auto &x : d) {
+      cudaSetDevice(x.device);
+      if (x.h) cudaStreamSynchronize(x.h->e.stream);
+      if (x.bnd) { cudaStreamSynchronize(x.bnd); cudaStreamDestroy(x.bnd); }
+      for (cudaEvent_t ev : {x.ev_main, x.ev_bu, x.ev_bp, x.ev_end, x.ev_sent})
+        if (ev) cudaEventDestroy(ev);
+      if (x.h) fw25_destroy(x.h);
+    }
+  }
+
+  void init(const fw25_problem &pb, const int32_t *device_ids, int n) {
+    const int nX = pb.nX, base = nX / n, rem = nX % n;
+    if (base < 2 * M) fw25::fail(1, "x-slabs would be thinner than two halos (16 planes): use fewer GPUs");
+    if (pb.ext_p || pb.ext_u || pb.ext_v || pb.ext_w) fw25::fail(1, "caller-owned state arrays need a single device");
+    const size_t row = pb.ndim == 3 ? (size_t)(pb.map_pitch > 0 ? pb.map_pitch : pb.nZ) * pb.nY
+                                    : (size_t)(pb.map_pitch > 0 ? pb.map_pitch : pb.nY);   // map elements per x plane
+    d.resize(n);
+    int lo = 0;
+    for (int r = 0; r < n; ++r) {
+      Dev &x = d[r];
+      x.device = device_ids[r];
+      x.own_lo = lo;
+      x.own_hi = lo + base + (r < rem ? 1 : 0);
+      x.has_lo = r > 0;
+      x.has_hi = r < n - 1;
+      x.gx0 = x.has_lo ? x.own_lo - M : 0;
+      x.gx1 = x.has_hi ? x.own_hi + M : nX;
+      lo = x.own_hi;
+      fw25_problem sub = pb;
+      sub.nX = x.gx1 - x.gx0;
+      const size_t off = (size_t)x.gx0 * row;
+      const float **maps[13] = {&sub.rho, &sub.K, &sub.beta, &sub.kappax, &sub.kappau, &sub.apmlx1, &sub.bpmlx1,
+                                &sub.apmlx2, &sub.bpmlx2, &sub.apmlu1, &sub.bpmlu1, &sub.apmlu2, &sub.bpmlu2};
+      for (auto m : maps)
+        if (*m) *m += off;
+      if (sub.dcmap) sub.dcmap += off;
+      fw25_slab sl{nX, x.gx0, x.own_lo, x.own_hi};
+      const int rc = fw25_create(&sub, &sl, x.device, &x.h);
+      if (rc) throw Fail{rc};
+      FW_CUDA(cudaSetDevice(x.device));
+      int lo_pri = 0, hi_pri = 0;
+      FW_CUDA(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
+      FW_CUDA(cudaStreamCreateWithPriority(&x.bnd, cudaStreamNonBlocking, hi_pri));
+      for (cudaEvent_t *ev : {&x.ev_main, &x.ev_bu, &x.ev_bp, &x.ev_end, &x.ev_sent})
+        FW_CUDA(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
+    }
+    for (int r = 0; r + 1 < n; ++r) {      // neighbours talk over NVLink when the platform allows it
+      const int a = d[r].device, b = d[r + 1].device;
+      int ab = 0, ba = 0;
+      if (a == b) continue;
+      cudaDeviceCanAccessPeer(&ab, a, b);
+      cudaDeviceCanAccessPeer(&ba, b, a);
+      if (ab) { cudaSetDevice(a); cudaDeviceEnablePeerAccess(b, 0); }
+      if (ba) { cudaSetDevice(b); cudaDeviceEnablePeerAccess(a, 0); }
+      cudaGetLastError();                  // cudaErrorPeerAccessAlreadyEnabled is fine; copies are staged otherwise
+    }
+  }
+
+  Engine &E(int r) { return d[r].h->e; }
+
+  // my outermost owned planes [lo, lo+w) of `name` -> the same global planes (ghosts) of neighbour `to`
+  void send_planes(int r, int to, int which, int g_lo, int w) {
+    Engine &src = E(r), &dst = E(to);
+    float *s = which < 0 ? src.F.p : src.F.q[which];
+    float *t_ = which < 0 ? dst.F.p : dst.F.q[which];
+    const size_t plane = (size_t)src.G.sA;
+    const size_t bytes = (size_t)w * plane * sizeof(float);
+    FW_CUDA(cudaMemcpyPeerAsync(t_ + (size_t)(g_lo - dst.gx0) * plane, d[to].device,
+                                s + (size_t)(g_lo - src.gx0) * plane, d[r].device, bytes, d[r].bnd));
+    halo_bytes += (int64_t)bytes;
+  }
+
+  // exchange after a sweep: ready[r] = event on r's boundary stream after which r's boundary planes are final and
+  // r's ghost planes are no longer being read
+  void exchange(bool velocities) {
+    const int n = (int)d.size();
+    for (int r = 0; r < n; ++r) {
+      Dev &x = d[r];
+      FW_CUDA(cudaSetDevice(x.device));
+      cudaEvent_t Dev::*ready = velocities ? &Dev::ev_bu : &Dev::ev_bp;
+      const int nd = E(r).ndim;
+      for (int side = 0; side < 2; ++side) {
+        if (side == 0 ? !x.has_lo : !x.has_hi) continue;
+        const int to = side == 0 ? r - 1 : r + 1;
+        FW_CUDA(cudaStreamWaitEvent(x.bnd, d[to].*ready, 0));
+        auto lo_of = [&](int w) { return side == 0 ? x.own_lo : x.own_hi - w; };
+        if (velocities) {
+          send_planes(r, to, 0, lo_of(M), M);                 // u: x-stencil of fd_p
+          if (nd == 3) send_planes(r, to, 1, lo_of(1), 1);    // v, w: cross terms only
+          send_planes(r, to, 2, lo_of(1), 1);
+        } else {
+          send_planes(r, to, -1, lo_of(M), M);                // p: x-stencil of fd_u
+        }
+      }
+      FW_CUDA(cudaEventRecord(x.ev_sent, x.bnd));
+    }
+    for (int r = 0; r < n; ++r) {
+      Dev &x = d[r];
+      FW_CUDA(cudaSetDevice(x.device));
+      if (x.has_lo) FW_CUDA(cudaStreamWaitEvent(x.bnd, d[r - 1].ev_sent, 0));
+      if (x.has_hi) FW_CUDA(cudaStreamWaitEvent(x.bnd, d[r + 1].ev_sent, 0));
+    }
+  }
+
+  template <class Fn>
+  void boundary(Dev &x, Fn &&fn) {
+    if (x.has_lo) fn(x.own_lo, std::min(x.own_lo + M, x.own_hi));
+    if (x.has_hi) fn(std::max(x.own_hi - M, x.own_lo), x.own_hi);
+  }
+
+  void step() {
+    const int n = (int)d.size();
+    for (int r = 0; r < n; ++r) {          // inject, boundary planes of fd_u first
+      Dev &x = d[r];
+      Engine &e = E(r);
+      FW_CUDA(cudaSetDevice(x.device));
+      if (t > 0) FW_CUDA(cudaStreamWaitEvent(e.stream, x.ev_end, 0));   // ghost p planes of the previous step are in
+      e.inject(t, e.stream);
+      FW_CUDA(cudaEventRecord(x.ev_main, e.stream));
+      FW_CUDA(cudaStreamWaitEvent(x.bnd, x.ev_main, 0));
+      boundary(x, [&](int lo, int hi) { e.sweep_u(lo, hi, x.bnd); });
+      FW_CUDA(cudaEventRecord(x.ev_bu, x.bnd));
+    }
+    exchange(true);
+    for (int r = 0; r < n; ++r) {          // interior fd_u overlaps the transfers; then boundary planes of fd_p
+      Dev &x = d[r];
+      Engine &e = E(r);
+      FW_CUDA(cudaSetDevice(x.device));
+      e.sweep_u(x.own_lo + (x.has_lo ? M : 0), x.own_hi - (x.has_hi ? M : 0), e.stream);
+      FW_CUDA(cudaEventRecord(x.ev_main, e.stream));
+      FW_CUDA(cudaStreamWaitEvent(x.bnd, x.ev_main, 0));
+      boundary(x, [&](int lo, int hi) { e.sweep_p(lo, hi, x.bnd); });
+      FW_CUDA(cudaEventRecord(x.ev_bp, x.bnd));
+    }
+    exchange(false);
+    for (int r = 0; r < n; ++r) {          // interior fd_p overlaps the p transfers
+      Dev &x = d[r];
+      Engine &e = E(r);
+      FW_CUDA(cudaSetDevice(x.device));
+      FW_CUDA(cudaEventRecord(x.ev_end, x.bnd));
+      FW_CUDA(cudaStreamWaitEvent(e.stream, x.ev_bu, 0));     // interior fd_p reads the boundary planes' velocities
+      e.sweep_p(x.own_lo + (x.has_lo ? M : 0), x.own_hi - (x.has_hi ? M : 0), e.stream);
+      if (t % e.modT == 0) {
+        FW_CUDA(cudaStreamWaitEvent(e.stream, x.ev_bp, 0));
+        e.record(t / e.modT, e.stream);
+      }
+      e.t = t + 1;
+    }
+    ++t;
+  }
+
+  void sync_all() {
+    for (auto &x : d) {
+      FW_CUDA(cudaSetDevice(x.device));
+      FW_CUDA(cudaStreamSynchronize(x.bnd));
+      FW_CUDA(cudaStreamSynchronize(x.h->e.stream));
+      FW_CUDA(cudaGetLastError());
+    }
+  }
+};
+
+int run_multi(const fw25_problem *pb, const int32_t *device_ids, int n, float *genout, fw25_stats *stats) {
+  using clk = std::chrono::steady_clock;
+  auto ms_since = [](clk::time_point a) { return std::chrono::duration<double, std::milli>(clk::now() - a).count(); };
+  MultiRun mr;
+  const auto t0 = clk::now();
+  mr.init(*pb, device_ids, n);
+  mr.sync_all();
+  const double setup_ms = ms_since(t0);
+  const int n_frames = n_frames_of(pb);
+  int cap = INT_MAX;
+  for (int r = 0; r < n; ++r) cap = std::min(cap, mr.E(r).frames_cap);
+  std::vector<float> tmp;
+  double d2h_ms = 0;
+  int flushed = 0;
+  auto flush = [&](int upto) {
+    const auto a = clk::now();
+    mr.sync_all();
+    for (int r = 0; r < n; ++r) {
+      FW_CUDA(cudaSetDevice(mr.d[r].device));
+      scatter_frames(mr.E(r), flushed, upto, genout, pb->ncoordsout, tmp);
+    }
+    flushed = upto;
+    d2h_ms += ms_since(a);
+  };
+  const auto t1 = clk::now();
+  double flush_in_loop = 0;
+  for (int t = 0; t < pb->nT; ++t) {
+    const int have = (t + pb->modT - 1) / pb->modT;          // frames recorded by steps 0 .. t-1
+    if (t % pb->modT == 0 && have - flushed >= cap) { const double b = d2h_ms; flush(have); flush_in_loop += d2h_ms - b; }
+    mr.step();
+  }
+  mr.sync_all();
+  const double loop_ms = ms_since(t1) - flush_in_loop;
+  flush(n_frames);
+  if (stats) {
+    stats->setup_ms = setup_ms;
+    stats->loop_ms = loop_ms;
+    stats->d2h_ms = d2h_ms;
+    stats->kernel_launches = 0;
+    stats->h2d_bytes = 0;
+    for (int r = 0; r < n; ++r) { stats->kernel_launches += mr.E(r).launches; stats->h2d_bytes += mr.E(r).h2d_bytes; }
+    stats->d2h_bytes = (int64_t)n_frames * pb->ncoordsout * 4;
+    stats->point_updates = (int64_t)pb->nX * pb->nY * (pb->ndim == 3 ? pb->nZ : 1) * (int64_t)pb->nT;
+    stats->halo_bytes = mr.halo_bytes;
+    stats->n_devices = n;
+  }
+  return 0;
+}
+
+// The time loop over an existing engine, from its current step to nT: frames are read out of the device ring when
+// it fills up and at the end.  genout: [n_frames][n_sens_global].
+void run_loop(Engine &e, float *genout, fw25_stats *stats, double setup_ms) {
+  struct Ev {
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    ~Ev() { for (auto x : ev) if (x) cudaEventDestroy(x); }
+  } H;
+  FW_CUDA(cudaSetDevice(e.device));
+  for (auto &x : H.ev) FW_CUDA(cudaEventCreate(&x));
+  std::vector<float> tmp;
+  double d2h_ms = 0, flush_in_loop = 0;
+  int flushed = 0;
+  const int64_t l0 = e.launches, h0 = e.h2d_bytes;
+  const int t_begin = e.t;
+  auto flush = [&](int upto) {
+    FW_CUDA(cudaEventRecord(H.ev[2], e.stream));
+    scatter_frames(e, flushed, upto, genout, e.n_sens_global, tmp);
+    FW_CUDA(cudaEventRecord(H.ev[3], e.stream));
+    FW_CUDA(cudaEventSynchronize(H.ev[3]));
+    float ms = 0;
+    FW_CUDA(cudaEventElapsedTime(&ms, H.ev[2], H.ev[3]));
+    d2h_ms += ms;
+    flushed = upto;
+  };
+  FW_CUDA(cudaEventRecord(H.ev[0], e.stream));
+  while (e.t < e.nT) {
+    const int have = (e.t + e.modT - 1) / e.modT;            // frames recorded by steps 0 .. t-1
+    int room = e.frames_cap - (have - flushed);
+    if (room <= 0 && e.t % e.modT == 0) { const double b = d2h_ms; flush(have); flush_in_loop += d2h_ms - b; room = e.frames_cap; }
+    e.advance(e.nT - e.t, room);
+  }
+  FW_CUDA(cudaEventRecord(H.ev[1], e.stream));
+  FW_CUDA(cudaEventSynchronize(H.ev[1]));
+  FW_CUDA(cudaGetLastError());
+  float loop_ms = 0;
+  FW_CUDA(cudaEventElapsedTime(&loop_ms, H.ev[0], H.ev[1]));
+  flush(e.n_frames);
+  if (stats) {
+    stats->setup_ms = setup_ms;
+    stats->loop_ms = loop_ms - flush_in_loop;
+    stats->d2h_ms = d2h_ms;
+    stats->kernel_launches = e.launches - l0;
+    stats->h2d_bytes = setup_ms > 0 ? e.h2d_bytes : e.h2d_bytes - h0;
+    stats->d2h_bytes = (int64_t)e.n_frames * e.n_sens * 4;
+    stats->point_updates = (int64_t)e.nXl * e.nY * e.nZ * (int64_t)(e.nT - t_begin);
+    stats->halo_bytes = 0;
+    stats->n_devices = 1;
+  }
+}
+
+int run_single(const fw25_problem *pb, int dev0, float *genout, fw25_stats *stats) {
+  struct Holder {
+    fw25_engine *h = nullptr;
+    ~Holder() { if (h) fw25_destroy(h); }
+  } H;
+  using clk = std::chrono::steady_clock;
+  const auto t0 = clk::now();
+  const int rc = fw25_create(pb, nullptr, dev0, &H.h);
+  if (rc) throw Fail{rc};
+  Engine &e = H.h->e;
+  FW_CUDA(cudaStreamSynchronize(e.stream));
+  const double setup_ms = std::chrono::duration<double, std::milli>(clk::now() - t0).count();
+  run_loop(e, genout, stats, setup_ms);
+  if (stats) stats->kernel_launches = e.launches;
+  return 0;
+}
+
+}  // namespace
+
 extern "C" {
 
 const char *fw25_last_error(void) { return g_err.c_str(); }
@@ -407,7 +872,7 @@ int fw25_record(fw25_engine *h, int32_t frame, void *s) { FW_TRY((cudaSetDevice(
 int fw25_step(fw25_engine *h, int32_t n) {
   FW_TRY({
     FW_CUDA(cudaSetDevice(h->e.device));
-    for (int i = 0; i < n; ++i) h->e.step_once();
+    for (int left = n; left > 0;) left -= h->e.advance(left, INT_MAX);
     FW_CUDA(cudaGetLastError());
   })
 }
@@ -421,8 +886,8 @@ int fw25_step_timed(fw25_engine *h, int32_t n, int32_t detail, double *out) {
     std::vector<cudaEvent_t> ev((size_t)(detail ? 4 * n : 0) + 2);
     for (auto &x : ev) FW_CUDA(cudaEventCreate(&x));
     FW_CUDA(cudaEventRecord(ev[0], e.stream));
-    for (int i = 0; i < n; ++i) {
-      if (!detail) { e.step_once(); continue; }
+    for (int left = detail ? 0 : n; left > 0;) left -= e.advance(left, INT_MAX);
+    for (int i = 0; i < (detail ? n : 0); ++i) {
       cudaEvent_t *q = &ev[2 + 4 * (size_t)i];
       e.inject(e.t, e.stream);
       FW_CUDA(cudaEventRecord(q[0], e.stream));
@@ -483,7 +948,7 @@ int32_t fw25_current_step(const fw25_engine *h) { return h->e.t; }
 int64_t fw25_launch_count(const fw25_engine *h) { return h->e.launches; }
 int fw25_set_kernel_variant(fw25_engine *h, int32_t v) {
   if (v < 0 || v > 3) { g_err = "fw25_set_kernel_variant: variant must be 0..3"; return 1; }
-  if (v == 2 && !h->e.plan) { g_err = "fw25_set_kernel_variant: the TMA-tiled sweeps need a 3D problem"; return 1; }
+  if (v == 2 && !h->e.plan && !h->e.p2d) { g_err = "fw25_set_kernel_variant: the TMA-tiled sweeps cannot run this problem"; return 1; }
   if (v == 3 && !h->e.ws) { g_err = "fw25_set_kernel_variant: the warp-specialised sweeps need a 3D problem with < 2^32 cells per array"; return 1; }
   h->e.variant = v;
   return 0;
@@ -492,84 +957,44 @@ int fw25_set_kernel_variant(fw25_engine *h, int32_t v) {
 int fw25_run(const fw25_problem *pb, const int32_t *device_ids, int32_t n_devices, float *genout,
              size_t genout_len, fw25_stats *stats) {
   if (!pb) { g_err = "fw25_run: NULL problem"; return 1; }
-  const int dev0 = (device_ids && n_devices > 0) ? device_ids[0] : 0;
-  if (n_devices > 1) { g_err = "fw25_run: in-process multi-device sharding is not built yet; use the torchrun driver"; return 4; }
-  const int n_frames = pb->nT > 0 ? (pb->nT + pb->modT - 1) / std::max(pb->modT, 1) : 0;
+  if (pb->modT <= 0) { g_err = "modT must be >= 1"; return 1; }
+  const int32_t dev0 = 0;
+  if (!device_ids || n_devices <= 0) { device_ids = &dev0; n_devices = 1; }
+  const int n_frames = n_frames_of(pb);
   if (genout_len < (size_t)n_frames * (size_t)std::max(pb->ncoordsout, 0)) {
     g_err = "fw25_run: genout buffer too small";
     return 1;
   }
-  if ((size_t)n_frames * pb->ncoordsout > 0 && !genout) { g_err = "fw25_run: NULL genout"; return 1; }
-  fw25_engine *h = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  int rc = 0;
+  if ((size_t)n_frames * std::max(pb->ncoordsout, 0) > 0 && !genout) { g_err = "fw25_run: NULL genout"; return 1; }
   try {
-    FW_CUDA(cudaSetDevice(dev0));
-    FW_CUDA(cudaEventCreate(&ev0));
-    FW_CUDA(cudaEventCreate(&ev1));
-    cudaEvent_t s0, s1;
-    FW_CUDA(cudaEventCreate(&s0));
-    FW_CUDA(cudaEventCreate(&s1));
-    FW_CUDA(cudaEventRecord(s0, 0));
-    rc = fw25_create(pb, nullptr, dev0, &h);
-    if (rc) throw Fail{rc};
-    Engine &e = h->e;
-    FW_CUDA(cudaEventRecord(s1, 0));
-    FW_CUDA(cudaEventSynchronize(s1));
-    float setup_ms = 0, loop_ms = 0;
-    FW_CUDA(cudaEventElapsedTime(&setup_ms, s0, s1));
-    cudaEventDestroy(s0); cudaEventDestroy(s1);
-    double d2h_ms = 0;
-    int flushed = 0;  // frames already copied out
-    FW_CUDA(cudaEventRecord(ev0, e.stream));
-    for (int t = 0; t < e.nT; ++t) {
-      e.step_once();
-      const int have = (t / e.modT) + 1;  // frames recorded so far
-      if (have - flushed == e.frames_cap && t % e.modT == 0 && have < e.n_frames) {
-        cudaEvent_t a, b;
-        FW_CUDA(cudaEventCreate(&a)); FW_CUDA(cudaEventCreate(&b));
-        FW_CUDA(cudaEventRecord(a, e.stream));
-        e.read_frames(flushed, have, genout + (size_t)flushed * e.n_sens);
-        FW_CUDA(cudaEventRecord(b, e.stream));
-        FW_CUDA(cudaEventSynchronize(b));
-        float ms = 0; cudaEventElapsedTime(&ms, a, b); d2h_ms += ms;
-        cudaEventDestroy(a); cudaEventDestroy(b);
-        flushed = have;
-      }
-    }
-    FW_CUDA(cudaEventRecord(ev1, e.stream));
-    FW_CUDA(cudaEventSynchronize(ev1));
-    FW_CUDA(cudaGetLastError());
-    FW_CUDA(cudaEventElapsedTime(&loop_ms, ev0, ev1));
-    {
-      cudaEvent_t a, b;
-      FW_CUDA(cudaEventCreate(&a)); FW_CUDA(cudaEventCreate(&b));
-      FW_CUDA(cudaEventRecord(a, e.stream));
-      e.read_frames(flushed, e.n_frames, genout + (size_t)flushed * e.n_sens);
-      FW_CUDA(cudaEventRecord(b, e.stream));
-      FW_CUDA(cudaEventSynchronize(b));
-      float ms = 0; cudaEventElapsedTime(&ms, a, b); d2h_ms += ms;
-      cudaEventDestroy(a); cudaEventDestroy(b);
-    }
-    if (stats) {
-      stats->setup_ms = setup_ms;
-      stats->loop_ms = loop_ms - (e.n_frames > e.frames_cap ? d2h_ms : 0.0);
-      stats->d2h_ms = d2h_ms;
-      stats->kernel_launches = e.launches;
-      stats->h2d_bytes = e.h2d_bytes;
-      stats->d2h_bytes = (int64_t)e.n_frames * e.n_sens * 4;
-      stats->point_updates = (int64_t)pb->nX * pb->nY * (pb->ndim == 3 ? pb->nZ : 1) * (int64_t)pb->nT;
-    }
+    if (n_devices > 1) return run_multi(pb, device_ids, n_devices, genout, stats);
+    return run_single(pb, device_ids[0], genout, stats);
   } catch (const Fail &f) {
-    rc = f.code;
+    return f.code;
   } catch (const std::exception &ex) {
     g_err = std::string("exception: ") + ex.what();
-    rc = 3;
+    return 3;
   }
-  if (h) fw25_destroy(h);
-  if (ev0) cudaEventDestroy(ev0);
-  if (ev1) cudaEventDestroy(ev1);
-  return rc;
+}
+
+int fw25_reset(fw25_engine *h, int32_t nT, int32_t nTic, int32_t ncoords, const int32_t *icc, const float *icmat) {
+  if (!h) { g_err = "fw25_reset: NULL engine"; return 1; }
+  FW_TRY((cudaSetDevice(h->e.device), h->e.reset(nT, nTic, ncoords, icc, icmat)))
+}
+
+int fw25_run_engine(fw25_engine *h, float *genout, size_t genout_len, fw25_stats *stats) {
+  if (!h) { g_err = "fw25_run_engine: NULL engine"; return 1; }
+  Engine &e = h->e;
+  if (e.own_lo != 0 || e.own_hi != e.nX_global) { g_err = "fw25_run_engine: the engine holds one slab of a sharded grid"; return 1; }
+  if (genout_len < (size_t)e.n_frames * (size_t)e.n_sens_global) { g_err = "fw25_run_engine: genout buffer too small"; return 1; }
+  if ((size_t)e.n_frames * e.n_sens_global > 0 && !genout) { g_err = "fw25_run_engine: NULL genout"; return 1; }
+  FW_TRY(run_loop(e, genout, stats, 0.0))
+}
+
+int32_t fw25_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
 }
 
 }  // extern "C"

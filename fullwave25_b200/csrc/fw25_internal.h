@@ -26,13 +26,25 @@ void ws_plan_destroy(WsPlan *pl);
 int launch_sweep_u_ws(const WsPlan *pl, const Fields &F, const Geom &G, int a_lo, int a_hi, cudaStream_t st);
 int launch_sweep_p_ws(const WsPlan *pl, const Fields &F, const Geom &G, int a_lo, int a_hi, cudaStream_t st);
 
+// TMA-tiled 2D sweeps: fw25_sweeps_2d.cu
+struct Plan2D;
+bool sweeps2d_supported(int ndim, const Geom &G);
+Plan2D *plan2d_create(const Fields &F, const Geom &G, const float *host_dmap, cudaStream_t st, std::string *err);
+void plan2d_destroy(Plan2D *pl);
+int launch_sweep_u_2d(const Plan2D *pl, const Fields &F, const Geom &G, int a_lo, int a_hi, cudaStream_t st);
+int launch_sweep_p_2d(const Plan2D *pl, const Fields &F, const Geom &G, int a_lo, int a_hi, cudaStream_t st);
+
 // point kernels: fw25_points.cu
 void launch_dcmap_mask(int32_t *dcmap, long long cells, int pitch, int nC, int nB, long long first_plane,
                        long long limit, cudaStream_t st);
 void launch_inject(float *p, const long long *src_idx, const int *src_row, const unsigned char *src_rim,
                    int n_src, const float *icmat, int nTic, int t, const long long *air_idx, int n_air,
-                   cudaStream_t st);
+                   cudaStream_t st, const int *d_t = nullptr);
 void launch_record(const float *p, const long long *sens_idx, int n_sens, float *frame, cudaStream_t st);
+// graph-replayed forms: the step number is *d_t + t_off (device-side counter, advanced by launch_tick)
+void launch_record_dev(const float *p, const long long *sens_idx, int n_sens, float *frames, const int *d_t, int t_off,
+                       int modT, int cap, cudaStream_t st);
+void launch_tick(int *d_t, int set, int add, cudaStream_t st);   // *d_t = (set >= 0 ? set : *d_t) + add
 int launches_per_inject(int n_src, int n_air, int t, int nTic, int n_src_rim);
 
 }  // namespace fw25

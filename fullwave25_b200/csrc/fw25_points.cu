@@ -11,19 +11,24 @@ namespace fw25 {
 
 // p[src] = icmat[row][t] while t < nTic (overwrite, not add); afterwards a source that sits in the
 // never-updated 8-cell rim falls back to 0 (the reference's proceed_time copies the zero new half
-// over it).  Air voxels are zeroed after the sources, as in the reference's launch order.
+// over it).  Air voxels are zeroed after the sources in the reference's launch order: a source that is
+// also an air voxel is therefore always 0 -- the host marks it dead (flag bit 1) so that injection and
+// zeroing can share ONE launch without a write race.  Threads [0, n_src) inject, [n_src, n_src + n_air) zero.
+// t = t_off, or *d_t + t_off when the step number lives on the device (steps replayed from a CUDA graph).
 __global__ void k_inject(float *__restrict__ p, const long long *__restrict__ src_idx,
-                         const int *__restrict__ src_row, const unsigned char *__restrict__ src_rim,
-                         int n_src, const float *__restrict__ icmat, int nTic, int t) {
+                         const int *__restrict__ src_row, const unsigned char *__restrict__ src_flag,
+                         int n_src, const float *__restrict__ icmat, int nTic, int t_off,
+                         const int *__restrict__ d_t, const long long *__restrict__ air_idx, int n_air) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_src) return;
-  if (t < nTic) p[src_idx[i]] = icmat[(size_t)src_row[i] * nTic + t];
-  else if (src_rim[i]) p[src_idx[i]] = 0.0f;
-}
-
-__global__ void k_zero(float *__restrict__ p, const long long *__restrict__ air_idx, int n_air) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n_air) p[air_idx[i]] = 0.0f;
+  if (i < n_src) {
+    const int t = d_t ? *d_t + t_off : t_off;
+    const unsigned char f = src_flag[i];
+    if (f & 2) return;
+    if (t < nTic) p[src_idx[i]] = icmat[(size_t)src_row[i] * nTic + t];
+    else if (f & 1) p[src_idx[i]] = 0.0f;
+  } else if (i < n_src + n_air) {
+    p[air_idx[i - n_src]] = 0.0f;
+  }
 }
 
 // frame[i] = p'[sensor_i]; sensors in the 8-cell rim (idx < 0) read 0.
@@ -34,6 +39,18 @@ __global__ void k_record(const float *__restrict__ p, const long long *__restric
   const long long s = sens_idx[i];
   frame[i] = s < 0 ? 0.0f : p[s];
 }
+
+// graph-replayed form: the frame slot comes from the device-side step counter, frame = ((*d_t + t_off) / modT) % cap
+__global__ void k_record_dev(const float *__restrict__ p, const long long *__restrict__ sens_idx, int n_sens,
+                             float *__restrict__ frames, const int *__restrict__ d_t, int t_off, int modT, int cap) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_sens) return;
+  const int f = ((*d_t + t_off) / modT) % cap;
+  const long long s = sens_idx[i];
+  frames[(size_t)f * n_sens + i] = s < 0 ? 0.0f : p[s];
+}
+
+__global__ void k_tick(int *d_t, int set, int add) { *d_t = (set >= 0 ? set : *d_t) + add; }
 
 // Reference 3D behaviour (include/fw25.h, dcmap_full3d): entries whose flat index in the WHOLE dense grid
 // ((x*nY + y)*nZ + z) is >= limit (= nX*nY) read 0.  Runs once at setup on the engine's padded copy.
@@ -57,21 +74,28 @@ void launch_dcmap_mask(int32_t *dcmap, long long cells, int pitch, int nC, int n
 }
 
 int launches_per_inject(int n_src, int n_air, int t, int nTic, int n_src_rim) {
-  int n = 0;
-  if (n_src > 0 && (t < nTic || n_src_rim > 0)) ++n;
-  if (n_air > 0) ++n;
-  return n;
+  return ((n_src > 0 && (t < nTic || n_src_rim > 0)) || n_air > 0) ? 1 : 0;
 }
 
-void launch_inject(float *p, const long long *src_idx, const int *src_row, const unsigned char *src_rim,
+// n_src = 0 skips the injection part (the caller passes 0 once t >= nTic and no source sits in the rim)
+void launch_inject(float *p, const long long *src_idx, const int *src_row, const unsigned char *src_flag,
                    int n_src, const float *icmat, int nTic, int t, const long long *air_idx, int n_air,
-                   cudaStream_t st) {
-  if (n_src > 0) k_inject<<<(n_src + 255) / 256, 256, 0, st>>>(p, src_idx, src_row, src_rim, n_src, icmat, nTic, t);
-  if (n_air > 0) k_zero<<<(n_air + 255) / 256, 256, 0, st>>>(p, air_idx, n_air);
+                   cudaStream_t st, const int *d_t) {
+  const int n = n_src + n_air;
+  if (n > 0)
+    k_inject<<<(n + 255) / 256, 256, 0, st>>>(p, src_idx, src_row, src_flag, n_src, icmat, nTic, t, d_t, air_idx, n_air);
 }
 
 void launch_record(const float *p, const long long *sens_idx, int n_sens, float *frame, cudaStream_t st) {
   if (n_sens > 0) k_record<<<(n_sens + 255) / 256, 256, 0, st>>>(p, sens_idx, n_sens, frame);
 }
+
+void launch_record_dev(const float *p, const long long *sens_idx, int n_sens, float *frames, const int *d_t, int t_off,
+                       int modT, int cap, cudaStream_t st) {
+  if (n_sens > 0)
+    k_record_dev<<<(n_sens + 255) / 256, 256, 0, st>>>(p, sens_idx, n_sens, frames, d_t, t_off, modT, cap);
+}
+
+void launch_tick(int *d_t, int set, int add, cudaStream_t st) { k_tick<<<1, 1, 0, st>>>(d_t, set, add); }
 
 }  // namespace fw25

@@ -1,0 +1,341 @@
+// fw25_sweeps_2d.cu -- 2D sweeps for sm_100a: TMA-staged stencil tiles, register-held x column.
+//
+// The 2D grids of the shipped examples are 0.4-3 M points: the whole problem lives in L2 or
+// nearly so, a step takes tens of microseconds, and there is no third axis to march along.  So the CTA is a
+// small tile -- RPT rows (x) by 128 columns (the contiguous axis) -- whose haloed stencil field arrives with ONE
+// TMA load (cp.async.bulk.tensor.2d, out-of-range elements zero-filled); each of the 128 threads owns one
+// column, keeps the 16-point x column in registers while it walks down the RPT rows (one new LDS per row), reads
+// the 15 taps along the contiguous axis and the cross-term neighbours from shared memory, and loads the
+// point-wise arrays (coefficients, memory variables, old fields: each touched exactly once) straight from
+// global memory, one row ahead of the arithmetic.  ncu on the one-thread-per-cell kernels this replaces
+// (profiles/ncu_r01_2d.txt): 400 instructions per 32 cells, ~36 global loads of p per cell through L1/L2,
+// long-scoreboard stalls of 19 warps per issue, DRAM at 41 %.
+//
+// Arithmetic: operation for operation the reference's (2D PTX L38-463 / L465-891; fw25_kernels.cuh);
+// bit-identical to k_sweep_*_simple<2> and the oracle.
+#include <cuda.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+#include "fw25_internal.h"
+#include "fw25_kernels.cuh"
+#include "fw25_tma.cuh"
+
+#ifndef FW25_WS_2D_MINB
+#define FW25_WS_2D_MINB 6   // resident CTAs per SM the register budget is sized for (80 registers, no spills)
+#endif
+
+namespace fw25 {
+
+namespace {
+
+constexpr int TC2 = 128;    // columns per CTA = threads per CTA
+
+struct StencilTab2 {
+  float4 d03, d47, e;
+};
+
+struct PwU {   // point-wise operands of one cell of fd_u
+  float rho, K, kx, a1, b1, a2, b2, mA1, mA2, mC1, mC2, qA, qC;
+  int ci;
+};
+
+__device__ __forceinline__ PwU load_pw_u(const Fields &F, long long i) {
+  PwU w;
+  w.ci = __ldg(F.dcmap + i);
+  w.rho = __ldg(F.rho + i); w.K = __ldg(F.K + i); w.kx = __ldg(F.kappax + i);
+  w.a1 = __ldg(F.ax1 + i); w.b1 = __ldg(F.bx1 + i); w.a2 = __ldg(F.ax2 + i); w.b2 = __ldg(F.bx2 + i);
+  w.mA1 = __ldcs(F.psi[0][0] + i); w.mA2 = __ldcs(F.psi[0][1] + i);
+  w.mC1 = __ldcs(F.psi[2][0] + i); w.mC2 = __ldcs(F.psi[2][1] + i);
+  w.qA = __ldcs(F.q[0] + i); w.qC = __ldcs(F.q[2] + i);
+  return w;
+}
+
+struct PwP {   // point-wise operands of one cell of fd_p
+  float K, beta, ku, a1, b1, a2, b2, fA1, fA2, fC1, fC2, p;
+  int ci;
+};
+
+__device__ __forceinline__ PwP load_pw_p(const Fields &F, long long i) {
+  PwP w;
+  w.ci = __ldg(F.dcmap + i);
+  w.K = __ldg(F.K + i); w.beta = __ldg(F.beta + i); w.ku = __ldg(F.kappau + i);
+  w.a1 = __ldg(F.au1 + i); w.b1 = __ldg(F.bu1 + i); w.a2 = __ldg(F.au2 + i); w.b2 = __ldg(F.bu2 + i);
+  w.fA1 = __ldcs(F.phi[0][0] + i); w.fA2 = __ldcs(F.phi[0][1] + i);
+  w.fC1 = __ldcs(F.phi[2][0] + i); w.fC2 = __ldcs(F.phi[2][1] + i);
+  w.p = F.p[i];
+  return w;
+}
+
+// ------------------------------------------------------------------------------------------ fd_u (2D)
+template <int RPT>
+__global__ void __launch_bounds__(TC2, FW25_WS_2D_MINB)
+    k_sweep_u_2d(const __grid_constant__ CUtensorMap map_p, const Fields F, const Geom G,
+                 const StencilTab2 *__restrict__ tab, int a_lo, int a_hi) {
+  constexpr int HR = RPT + 15, HC = TC2 + 16;
+  __shared__ alignas(128) float tile[HR][HC];   // tile[r][j] = p[a0 - 7 + r][c0 - 8 + j]
+  __shared__ uint64_t bar;
+  const int tc = threadIdx.x;
+  const int c0 = blockIdx.x * TC2;
+  const int a0 = a_lo + blockIdx.y * RPT;
+  if (tc == 0) {
+    mbar_init(&bar, 1);
+    mbar_fence_init();
+    mbar_arrive_expect_tx(&bar, HR * HC * 4);
+    tma_load_2d(&tile[0][0], &map_p, c0 - 8, a0 - 7, &bar);
+  }
+  __syncthreads();                               // the initialised barrier is visible to every waiter
+
+  const int c = c0 + tc;
+  const bool act = c >= M && c < G.nC - M;
+  const int rows = min(RPT, a_hi - a0);
+  long long i = (long long)a0 * G.sA + c;
+  PwU cur{};
+  if (act) cur = load_pw_u(F, i);                // row 0's operands fly while the tile lands
+  mbar_wait(&bar, 0);
+  if (!act) return;
+
+  const int sc = tc + 8;
+  float pc[16];                                  // pc[j] = p[a - 7 + j][c]
+#pragma unroll
+  for (int j = 0; j < 15; ++j) pc[j + 1] = tile[j][sc];
+
+#pragma unroll
+  for (int r = 0; r < RPT; ++r) {
+    if (r >= rows) break;
+    const int sr = r + 7;
+#pragma unroll
+    for (int j = 0; j < 15; ++j) pc[j] = pc[j + 1];
+    pc[15] = tile[sr + 8][sc];
+    PwU nxt{};
+    if (r + 1 < rows) nxt = load_pw_u(F, i + G.sA);
+
+    const StencilTab2 T = tab[cur.ci];
+    const float D[9] = {0.f, T.d03.x, T.d03.y, T.d03.z, T.d03.w, T.d47.x, T.d47.y, T.d47.z, T.d47.w};
+    const float E = T.e.x;
+    float yv[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) yv[j] = (j == 7) ? pc[7] : tile[sr][sc + j - 7];
+    float gA = 0.f, gC = 0.f;
+#pragma unroll
+    for (int k = 1; k <= M; ++k) {
+      gA = fma_(D[k], sub_(pc[7 + k], pc[8 - k]), gA);
+      gC = fma_(D[k], sub_(yv[7 + k], yv[8 - k]), gC);
+    }
+    const float p11 = tile[sr + 1][sc + 1];
+    float cA = sub_(p11, yv[8]);
+    cA = add_(cA, tile[sr + 1][sc - 1]); cA = sub_(cA, yv[6]);
+    float cC = sub_(p11, pc[8]);
+    cC = add_(cC, tile[sr - 1][sc + 1]); cC = sub_(cC, pc[6]);
+    const float dX = G.dX;
+    gA = div_(fma_(E, cA, gA), dX);
+    gC = div_(fma_(E, cC, gC), dX);
+
+    const float s = div_(div_(G.dT, cur.rho), fma_(rcp_(cur.K), pc[7], 1.0f));
+    const float mA1 = fma_(cur.b1, cur.mA1, mul_(gA, cur.a1));
+    const float mA2 = fma_(cur.b2, cur.mA2, mul_(gA, cur.a2));
+    const float mC1 = fma_(cur.b1, cur.mC1, mul_(gC, cur.a1));
+    const float mC2 = fma_(cur.b2, cur.mC2, mul_(gC, cur.a2));
+    const float qA = fma_(-s, add_(add_(div_(gA, cur.kx), mA1), mA2), cur.qA);
+    const float qC = fma_(-s, add_(add_(div_(gC, cur.kx), mC1), mC2), cur.qC);
+    __stcs(F.psi[0][0] + i, mA1); __stcs(F.psi[0][1] + i, mA2);
+    __stcs(F.psi[2][0] + i, mC1); __stcs(F.psi[2][1] + i, mC2);
+    F.q[0][i] = qA; F.q[2][i] = qC;              // the next sweep's stencil fields: default caching
+    cur = nxt;
+    i += G.sA;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ fd_p (2D)
+template <int RPT>
+__global__ void __launch_bounds__(TC2, FW25_WS_2D_MINB)
+    k_sweep_p_2d(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_v, const Fields F,
+                 const Geom G, const StencilTab2 *__restrict__ tab, int a_lo, int a_hi) {
+  constexpr int UR = RPT + 15, UC = TC2 + 8;     // tu[r][j] = u[a0 - 8 + r][c0 - 4 + j]
+  constexpr int VR = RPT + 2, VC = TC2 + 16;     // tv[r][j] = v[a0 - 1 + r][c0 - 8 + j]
+  __shared__ alignas(128) float tu[UR][UC];
+  __shared__ alignas(128) float tv[VR][VC];
+  __shared__ uint64_t bar;
+  const int tc = threadIdx.x;
+  const int c0 = blockIdx.x * TC2;
+  const int a0 = a_lo + blockIdx.y * RPT;
+  if (tc == 0) {
+    mbar_init(&bar, 1);
+    mbar_fence_init();
+    mbar_arrive_expect_tx(&bar, (UR * UC + VR * VC) * 4);
+    tma_load_2d(&tu[0][0], &map_u, c0 - 4, a0 - 8, &bar);
+    tma_load_2d(&tv[0][0], &map_v, c0 - 8, a0 - 1, &bar);
+  }
+  __syncthreads();
+
+  const int c = c0 + tc;
+  const bool act = c >= M && c < G.nC - M;
+  const int rows = min(RPT, a_hi - a0);
+  long long i = (long long)a0 * G.sA + c;
+  PwP cur{};
+  if (act) cur = load_pw_p(F, i);
+  mbar_wait(&bar, 0);
+  if (!act) return;
+
+  const int su = tc + 4, sv = tc + 8;
+  float uc[16];                                  // uc[j] = u[a - 8 + j][c]
+#pragma unroll
+  for (int j = 0; j < 15; ++j) uc[j + 1] = tu[j][su];
+
+#pragma unroll
+  for (int r = 0; r < RPT; ++r) {
+    if (r >= rows) break;
+    const int ur = r + 8, vr = r + 1;
+#pragma unroll
+    for (int j = 0; j < 15; ++j) uc[j] = uc[j + 1];
+    uc[15] = tu[ur + 7][su];
+    PwP nxt{};
+    if (r + 1 < rows) nxt = load_pw_p(F, i + G.sA);
+
+    const StencilTab2 T = tab[cur.ci];
+    const float D[9] = {0.f, T.d03.x, T.d03.y, T.d03.z, T.d03.w, T.d47.x, T.d47.y, T.d47.z, T.d47.w};
+    const float E = T.e.x;
+    float hA = 0.f, hC = 0.f;
+#pragma unroll
+    for (int k = 1; k <= M; ++k) {
+      hA = fma_(D[k], sub_(uc[7 + k], uc[8 - k]), hA);
+      hC = fma_(D[k], sub_(tv[vr][sv + k - 1], tv[vr][sv - k]), hC);
+    }
+    float cA = sub_(tu[ur][su + 1], tu[ur - 1][su + 1]);
+    cA = add_(cA, tu[ur][su - 1]); cA = sub_(cA, tu[ur - 1][su - 1]);
+    float cC = sub_(tv[vr + 1][sv], tv[vr + 1][sv - 1]);
+    cC = add_(cC, tv[vr - 1][sv]); cC = sub_(cC, tv[vr - 1][sv - 1]);
+    const float dX = G.dX;
+    hA = div_(fma_(E, cA, hA), dX);
+    hC = div_(fma_(E, cC, hC), dX);
+
+    const float fA1 = fma_(cur.b1, cur.fA1, mul_(hA, cur.a1));
+    const float fA2 = fma_(cur.b2, cur.fA2, mul_(hA, cur.a2));
+    const float fC1 = fma_(cur.b1, cur.fC1, mul_(hC, cur.a1));
+    const float fC2 = fma_(cur.b2, cur.fC2, mul_(hC, cur.a2));
+    float S = add_(div_(hA, cur.ku), div_(hC, cur.ku));
+    S = add_(fA1, S); S = add_(fA2, S); S = add_(fC1, S); S = add_(fC2, S);
+    const float At = mul_(mul_(G.dT, cur.K), S);
+    const float Bt = fma_(cur.p, mul_(rcp_(cur.K), sub_(1.0f, add_(cur.beta, cur.beta))), 1.0f);
+    __stcs(F.phi[0][0] + i, fA1); __stcs(F.phi[0][1] + i, fA2);
+    __stcs(F.phi[2][0] + i, fC1); __stcs(F.phi[2][1] + i, fC2);
+    F.p[i] = fma_(-At, Bt, cur.p);
+    cur = nxt;
+    i += G.sA;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host
+using EncodeFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                              const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                              CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeFn encode_fn_2d() {
+  static EncodeFn fn = [] {
+    void *sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      return reinterpret_cast<EncodeFn>(sym);
+    return (EncodeFn) nullptr;
+  }();
+  return fn;
+}
+
+bool tmap2d(CUtensorMap *m, const void *base, const Geom &G, int box_c, int box_a, std::string *err) {
+  EncodeFn fn = encode_fn_2d();
+  if (!fn) { *err = "cuTensorMapEncodeTiled is not available from this driver"; return false; }
+  const cuuint64_t dims[2] = {(cuuint64_t)G.pitch, (cuuint64_t)G.nA};
+  const cuuint64_t strides[1] = {(cuuint64_t)G.sA * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)box_c, (cuuint32_t)box_a};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char b[160];
+    snprintf(b, sizeof b, "cuTensorMapEncodeTiled (2D) failed with CUresult %d (pitch %d, box %dx%d)", (int)r, G.pitch,
+             box_c, box_a);
+    *err = b;
+    return false;
+  }
+  return true;
+}
+
+}  // namespace
+
+struct Plan2D {
+  StencilTab2 *tab = nullptr;
+  CUtensorMap p[2], u[2], v[2];   // [0]: RPT = 4, [1]: RPT = 8
+};
+
+bool sweeps2d_supported(int ndim, const Geom &G) {
+  return ndim == 2 && G.nB == 1 && G.pitch % 32 == 0 && G.nC > 2 * M && encode_fn_2d() != nullptr;
+}
+
+Plan2D *plan2d_create(const Fields &F, const Geom &G, const float *host_dmap, cudaStream_t st, std::string *err) {
+  auto *pl = new Plan2D();
+  bool ok = true;
+  for (int v = 0; v < 2 && ok; ++v) {
+    const int rpt = v ? 8 : 4;
+    ok = tmap2d(&pl->p[v], F.p, G, TC2 + 16, rpt + 15, err) && tmap2d(&pl->u[v], F.q[0], G, TC2 + 8, rpt + 15, err) &&
+         tmap2d(&pl->v[v], F.q[2], G, TC2 + 16, rpt + 2, err);
+  }
+  if (!ok) { delete pl; return nullptr; }
+  const int nd = G.ndmap;
+  std::vector<StencilTab2> t(nd);
+  for (int c = 0; c < nd; ++c) {
+    auto Dk = [&](int k) { return host_dmap[(size_t)(2 * k) * nd + c]; };
+    t[c].d03 = make_float4(Dk(1), Dk(2), Dk(3), Dk(4));
+    t[c].d47 = make_float4(Dk(5), Dk(6), Dk(7), Dk(8));
+    t[c].e = make_float4(host_dmap[(size_t)3 * nd + c], 0.f, 0.f, 0.f);
+  }
+  if (cudaMalloc(&pl->tab, sizeof(StencilTab2) * nd) != cudaSuccess ||
+      cudaMemcpyAsync(pl->tab, t.data(), sizeof(StencilTab2) * nd, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+      cudaStreamSynchronize(st) != cudaSuccess) {
+    *err = std::string("2D sweep plan: ") + cudaGetErrorString(cudaGetLastError());
+    if (pl->tab) cudaFree(pl->tab);
+    delete pl;
+    return nullptr;
+  }
+  return pl;
+}
+
+void plan2d_destroy(Plan2D *pl) {
+  if (!pl) return;
+  if (pl->tab) cudaFree(pl->tab);
+  delete pl;
+}
+
+// rows per CTA: 8 when that still gives every SM several waves of CTAs, else 4 (small grids need the parallelism
+// more than they need the shorter halo); FW25_2D_RPT overrides
+static int pick_rpt(const Geom &G, int rows) {
+  const char *ev = getenv("FW25_2D_RPT");
+  const int env = ev ? atoi(ev) : 0;
+  if (env == 4 || env == 8) return env;
+  const long long ctas8 = (long long)((G.nC - M + TC2 - 1) / TC2) * ((rows + 7) / 8);
+  return ctas8 >= 148LL * FW25_WS_2D_MINB * 2 ? 8 : 4;
+}
+
+int launch_sweep_u_2d(const Plan2D *pl, const Fields &F, const Geom &G, int a_lo, int a_hi, cudaStream_t st) {
+  if (a_hi <= a_lo) return 0;
+  const int rpt = pick_rpt(G, a_hi - a_lo);
+  dim3 grd((G.nC - M + TC2 - 1) / TC2, (a_hi - a_lo + rpt - 1) / rpt, 1);
+  if (rpt == 8) k_sweep_u_2d<8><<<grd, TC2, 0, st>>>(pl->p[1], F, G, pl->tab, a_lo, a_hi);
+  else k_sweep_u_2d<4><<<grd, TC2, 0, st>>>(pl->p[0], F, G, pl->tab, a_lo, a_hi);
+  return 1;
+}
+
+int launch_sweep_p_2d(const Plan2D *pl, const Fields &F, const Geom &G, int a_lo, int a_hi, cudaStream_t st) {
+  if (a_hi <= a_lo) return 0;
+  const int rpt = pick_rpt(G, a_hi - a_lo);
+  dim3 grd((G.nC - M + TC2 - 1) / TC2, (a_hi - a_lo + rpt - 1) / rpt, 1);
+  if (rpt == 8) k_sweep_p_2d<8><<<grd, TC2, 0, st>>>(pl->u[1], pl->v[1], F, G, pl->tab, a_lo, a_hi);
+  else k_sweep_p_2d<4><<<grd, TC2, 0, st>>>(pl->u[0], pl->v[0], F, G, pl->tab, a_lo, a_hi);
+  return 1;
+}
+
+}  // namespace fw25

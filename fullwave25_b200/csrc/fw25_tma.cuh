@@ -53,6 +53,15 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, i
       : "memory");
 }
 
+// 2-D tiled load: box origin (c0 = fastest axis, c1); out-of-bounds elements are written as zeros.
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(smem_addr(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_addr(bar))
+      : "memory");
+}
+
 // L2 eviction policies for TMA loads: streamed-once data should not push the stencil planes out of L2
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {
   uint64_t pol;

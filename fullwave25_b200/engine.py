@@ -49,7 +49,8 @@ class CSlab(C.Structure):
 class CStats(C.Structure):
     _fields_ = [("setup_ms", C.c_double), ("loop_ms", C.c_double), ("d2h_ms", C.c_double),
                 ("kernel_launches", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
-                ("point_updates", C.c_int64)]
+                ("point_updates", C.c_int64), ("halo_bytes", C.c_int64), ("n_devices", C.c_int32),
+                ("reserved_", C.c_int32)]
 
 
 _lib = None
@@ -74,6 +75,9 @@ _SIGS = {
     "fw25_current_step": (C.c_int32, [C.c_void_p]),
     "fw25_launch_count": (C.c_int64, [C.c_void_p]),
     "fw25_set_kernel_variant": (C.c_int, [C.c_void_p, C.c_int32]),
+    "fw25_reset": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, _I, _F]),
+    "fw25_run_engine": (C.c_int, [C.c_void_p, _F, C.c_size_t, C.POINTER(CStats)]),
+    "fw25_device_count": (C.c_int32, []),
     "fw25_last_error": (C.c_char_p, []),
     "fw25_abi_version": (C.c_int32, []),
 }
@@ -139,13 +143,10 @@ def marshal(pb: Problem, *, device_maps: dict | None = None, ext_state: dict | N
 
 
 def run(pb: Problem, device_ids=(0,)) -> tuple[np.ndarray, dict]:
-    """Whole job with HOST buffers.  One device: fw25_run (C-ABI).  Several devices (the reference's
-    `cuda_device_id=[0, 1, ...]`): x-slabs driven from this process with peer-to-peer halo copies
-    (runtime.run_local).  Returns (genout [n_frames, ncoordsout], stats)."""
+    """Whole job with HOST buffers through fw25_run (C-ABI).  Several devices (the reference's
+    `cuda_device_id=[0, 1, ...]`): x-slabs driven from this process by the native runner with peer-to-peer
+    halo copies.  Returns (genout [n_frames, ncoordsout], stats)."""
     pb.normalise()
-    if len(device_ids) > 1:
-        from . import runtime
-        return runtime.run_local(pb, list(device_ids), return_stats=True)
     s, keep = marshal(pb)
     genout = np.zeros((pb.n_frames, pb.ncoordsout), np.float32)
     ids = np.asarray(list(device_ids), np.int32)
@@ -187,6 +188,24 @@ class Engine:
 
     def __exit__(self, *exc):
         self.close()
+
+    def reset(self, icc: np.ndarray, icmat: np.ndarray, nT: int | None = None) -> None:
+        """Next transmit event on the same medium (fw25_reset): zero wave field, t = 0, new sources
+        icc int32 [ncoords, ndim], icmat float32 [ncoords, nTic]; maps and sensors stay on the device."""
+        icc = np.ascontiguousarray(icc, np.int32).reshape(-1, self.pb.ndim)
+        icmat = np.ascontiguousarray(icmat, np.float32).reshape(len(icc), -1)
+        nT = self.pb.nT if nT is None else int(nT)
+        _check(lib().fw25_reset(self._h, nT, icmat.shape[1], len(icc), icc.ctypes.data_as(_I), icmat.ctypes.data_as(_F)))
+        self._nT = nT
+
+    def run(self) -> tuple[np.ndarray, dict]:
+        """Steps [t, nT) with the frames read back (fw25_run_engine) -> (genout [n_frames, ncoordsout], stats)."""
+        nT = getattr(self, "_nT", self.pb.nT)
+        n_frames = -(-nT // self.pb.modT) if nT > 0 else 0
+        genout = np.zeros((n_frames, self.pb.ncoordsout), np.float32)
+        st = CStats()
+        _check(lib().fw25_run_engine(self._h, genout.ctypes.data_as(_F), genout.size, C.byref(st)))
+        return genout, {f: getattr(st, f) for f, _ in CStats._fields_}
 
     def set_variant(self, v: int) -> None:
         _check(lib().fw25_set_kernel_variant(self._h, v))

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define FW25_ABI_VERSION 2
+#define FW25_ABI_VERSION 3
 #define FW25_M 8 /* stencil half-width: solver.py:296 (m_spatial_order = 8), kernels launched with M = 8 */
 
 /* One simulation = the contents of one reference "simulation_dir".
@@ -79,6 +79,9 @@ typedef struct fw25_stats {
   int64_t kernel_launches;    /* kernels launched inside the time loop */
   int64_t h2d_bytes, d2h_bytes;
   int64_t point_updates;      /* nX*nY*nZ * nT (extended grid, the reference's count) */
+  int64_t halo_bytes;         /* bytes moved between x-slabs (all interfaces, both directions); 0 on one device */
+  int32_t n_devices;
+  int32_t reserved_;
 } fw25_stats;
 
 typedef struct fw25_engine fw25_engine; /* opaque */
@@ -96,6 +99,15 @@ int fw25_run(const fw25_problem *pb, const int32_t *device_ids, int32_t n_device
  * loop, kept alive so a caller can step, read fields and reuse uploads. */
 int fw25_create(const fw25_problem *pb, const fw25_slab *slab, int32_t device, fw25_engine **out);
 void fw25_destroy(fw25_engine *e);
+
+/* ---- several transmit events on one medium.  Upstream this is `Solver.run(is_static_map=True,
+ * recalculate_pml=False)` in a loop: only icmat.dat is rewritten per event, the maps are symlinked
+ * (input_file_writer.py:146-175, :647-714) -- and still re-read and re-uploaded by every launch of the binary.
+ * fw25_reset starts the next event on a live engine: wave field zeroed, t = 0, new source list and step counts;
+ * maps, stencil tables, sensors stay resident in HBM.  fw25_run_engine then runs steps [t, nT) and writes
+ * genout [ceil(nT/modT)][ncoordsout] like fw25_run (whole-grid engines only). */
+int fw25_reset(fw25_engine *e, int32_t nT, int32_t nTic, int32_t ncoords, const int32_t *icc, const float *icmat);
+int fw25_run_engine(fw25_engine *e, float *genout, size_t genout_len, fw25_stats *stats);
 
 /* One reference time step is: inject(t) -> sweep_u -> sweep_p -> record(t) when t % modT == 0
  * (SURVEY.md 3.3).  x ranges are GLOBAL and are clamped to the engine's owned range. stream is a
@@ -127,6 +139,10 @@ int64_t fw25_launch_count(const fw25_engine *e);
  * x-marching, 3 = warp-specialised all-TMA x-marching
  * (3D only; fails with an error if the variant cannot run the problem) */
 int fw25_set_kernel_variant(fw25_engine *e, int32_t variant);
+
+/* number of CUDA devices visible to this process: the executable drop-in shards over all of them, like the
+ * reference binary does with CUDA_VISIBLE_DEVICES (launcher.py:206; binary: cudaGetDeviceCount in main) */
+int32_t fw25_device_count(void);
 
 const char *fw25_last_error(void);
 int32_t fw25_abi_version(void);

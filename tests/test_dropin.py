@@ -101,3 +101,55 @@ def test_solver_run_identical_through_every_boundary(built_lib, shape):
     for name, got in out.items():
         assert got.shape == want.shape, name
         np.testing.assert_array_equal(got, want, err_msg=name)
+
+
+@needs_ref
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(40, 48), (20, 24, 28)])
+def test_static_map_transmit_events_reuse_device_maps(built_lib, shape):
+    """The reference's multi-transmit loop -- a new Solver per event, run(is_static_map=True, recalculate_pml=k==0)
+    -- through launcher.install(): the second and third events reuse the engine of the first (maps stay in HBM,
+    only the sources are replaced) and still match the reference binary event by event; so does the no-disk
+    Session path.
+
+    Reference behaviour pinned here: in static-map mode the reference does NOT link icczero.dat / ncoordszero.dat
+    into the simulation directory (input_file_writer.py:647-706 lists the linked files), so its binary -- and
+    any engine that honours the directory -- runs WITHOUT the air voxels; the no-disk Session path takes the air
+    map from the medium object and therefore matches the reference's non-static runs."""
+    from fullwave25_b200 import build
+    fw, grid, medium, source, sensor = ref_objects.build(shape, n_steps=48, n_sensors=10, n_air=4, modT=2)
+    kw = dict(pml_layer_thickness_px=6, n_transition_layer=4)
+    ndim = len(shape)
+    p0 = np.asarray(source.p0)
+    sources = [source, fw.Source(-0.5 * p0, source.mask), fw.Source(np.roll(p0, 5, axis=1), source.mask)]
+
+    def events(td, bin_path, static=True):
+        outs, launchers = [], []
+        for k, src in enumerate(sources):
+            s = fw.Solver(Path(td), grid, medium, src, sensor, path_fullwave_simulation_bin=bin_path, **kw)
+            outs.append(s.run(f"txrx_{k}", is_static_map=static, recalculate_pml=(k == 0) or not static))
+            launchers.append(s.fullwave_launcher)
+        return outs, launchers
+
+    with tempfile.TemporaryDirectory() as td_ref, tempfile.TemporaryDirectory() as td_new, \
+            tempfile.TemporaryDirectory() as td_full:
+        want, _ = events(td_ref, ref_objects.ref_bin(ndim))
+        want_air, _ = events(td_full, ref_objects.ref_bin(ndim), static=False)
+        undo = launcher.install()
+        try:
+            got, las = events(td_new, build.CLI)
+        finally:
+            undo()
+            launcher.release()
+        assert [la.last_stats["maps_reused"] for la in las] == [False, True, True]
+        with launcher.Session() as ses:
+            nodisk = []
+            for src in sources:
+                s = fw.Solver(Path(td_new) / "nodisk", grid, medium, src, sensor,
+                              path_fullwave_simulation_bin=build.CLI, **kw)
+                nodisk.append(launcher.run_solver(s, session=ses))
+    assert np.abs(want[0]).max() > 0 and not np.array_equal(want[0], want[1])
+    assert not np.array_equal(want[0], want_air[0])          # the static-map directory lost the air voxels
+    for k in range(3):
+        np.testing.assert_array_equal(got[k], want[k], err_msg=f"event {k} (launcher.install, static maps)")
+        np.testing.assert_array_equal(nodisk[k], want_air[k], err_msg=f"event {k} (Session)")

@@ -46,10 +46,10 @@ def test_run_matches_reference_golden_bit_exact(built_lib, name):
 @pytest.mark.parametrize("variant", [1, 2, 3])
 @pytest.mark.parametrize("name", ["het3d", "het2d", "het3d_ragged", "het3d_long"])
 def test_final_fields_match_oracle(built_lib, name, variant):
-    """variant 1 = simple sweeps, 2 = TMA-tiled x-marching, 3 = warp-specialised all-TMA (2 and 3: 3D only)."""
+    """variant 1 = simple sweeps, 2 = TMA-tiled (3D: x-marching; 2D: row tiles), 3 = warp-specialised all-TMA (3D only)."""
     pb = cases.make(name)
-    if variant >= 2 and pb.ndim == 2:
-        pytest.skip("tiled sweeps are 3D")
+    if variant == 3 and pb.ndim == 2:
+        pytest.skip("the warp-specialised sweeps are 3D")
     _, want = oracle.run(pb, return_fields=True)
     with engine.Engine(pb, variant=variant) as e:
         e.step(pb.nT)
@@ -99,6 +99,37 @@ def test_edge_cases(built_lib):
     pb = cases.make("het2d")
     pb.nT = 0
     assert engine.run(pb)[0].shape == (0, pb.ncoordsout)
+    # a source that is also an air voxel: zeroing follows injection in the reference's launch order, so it reads 0
+    for name in ("het2d", "het3d"):
+        pb = cases.make(name)
+        pb.icczero = np.vstack([pb.icczero, pb.icc[:3]]).astype(np.int32)
+        pb.outc = np.vstack([pb.outc, pb.icc[:4]]).astype(np.int32)
+        got = engine.run(pb)[0]
+        np.testing.assert_array_equal(got, oracle.run(pb))
+
+
+@pytest.mark.parametrize("name", ["het2d_long", "het3d_long", "het2d_ragged", "hom3d"])
+def test_graph_replayed_steps_equal_launched_steps(built_lib, name, monkeypatch):
+    """Whole steps replayed from a CUDA graph (device-side step counter) == the same steps launched one by one:
+    sensor frames (incl. a run that stops inside a recording period) and final fields."""
+    pb = cases.make(name)
+    pb.nT -= 3
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("FW25_GRAPH", mode)
+        g, st = engine.run(pb)
+        with engine.Engine(pb) as e:
+            e.step(7)                      # a partial period first, then the rest
+            e.step(pb.nT - 7)
+            e.sync()
+            out[mode] = (g, st["kernel_launches"], e.read_frames(0, pb.n_frames), {k: e.field(k) for k in "puv"})
+    np.testing.assert_array_equal(out["0"][0], out["1"][0])
+    np.testing.assert_array_equal(out["0"][2], out["1"][2])
+    np.testing.assert_array_equal(out["0"][0], out["0"][2])
+    for k in "puv":
+        np.testing.assert_array_equal(out["0"][3][k], out["1"][3][k], err_msg=k)
+    np.testing.assert_array_equal(out["1"][0], oracle.run(pb))
+    assert out["1"][1] >= 2 * pb.nT
 
 
 def test_errors_are_reported_not_swallowed(built_lib):
@@ -126,3 +157,20 @@ def test_mid_size_ragged_grid_all_variants_and_oracle(built_lib):
             for k in "puvw":
                 np.testing.assert_array_equal(e.field(k), want[k], err_msg=f"variant {variant} field {k}")
             np.testing.assert_array_equal(e.read_frames(0, pb.n_frames), want_g, err_msg=f"variant {variant}")
+
+
+@pytest.mark.parametrize("shape", [(203, 269), (61, 1031), (300, 40)])
+def test_2d_ragged_grids_tiled_and_simple_sweeps(built_lib, shape, monkeypatch):
+    """2D grids that are not multiples of the 128-column / 4- or 8-row tiles: TMA-tiled 2D sweeps (both tile
+    heights) == one-thread-per-cell sweeps == oracle, frames and final fields."""
+    from fullwave25_b200 import synthetic
+    pb = synthetic.make_problem(shape, nT=90, modT=4, seed=31, n_pml=9, n_trans=5, block=7, n_sensors=120, n_air=20)
+    want_g, want = oracle.run(pb, return_fields=True)
+    for variant, rpt in ((1, "0"), (2, "4"), (2, "8"), (0, "0")):
+        monkeypatch.setenv("FW25_2D_RPT", rpt)
+        with engine.Engine(pb, variant=variant) as e:
+            e.step(pb.nT)
+            e.sync()
+            for k in "puv":
+                np.testing.assert_array_equal(e.field(k), want[k], err_msg=f"variant {variant} rpt {rpt} field {k}")
+            np.testing.assert_array_equal(e.read_frames(0, pb.n_frames), want_g, err_msg=f"variant {variant} rpt {rpt}")

@@ -32,14 +32,43 @@ def test_two_gpus_bit_identical_to_one_domain(built_lib, case):
     assert verdict["bit_exact"] and verdict["absmax"] > 0, verdict
 
 
+@pytest.mark.parametrize("mode", ["native", "torch"])
 @pytest.mark.parametrize("case", ["het3d", "het2d_long"])
-def test_in_process_device_list_bit_identical(built_lib, case):
-    """`engine.run(pb, device_ids=(0, 1))` -- what Launcher(cuda_device_id=[0, 1]) calls -- one host thread, two GPUs."""
+def test_in_process_device_list_bit_identical(built_lib, case, mode):
+    """`engine.run(pb, device_ids=(0, 1))` -- what Launcher(cuda_device_id=[0, 1]) calls -- one host thread, two
+    GPUs: fw25_run's native multi-device runner, and the Python lockstep driver over the same C-ABI pieces."""
     if _n_gpus() < 2:
         pytest.skip("needs 2 GPUs")
-    r = subprocess.run([sys.executable, str(ROOT / "tools" / "slab_check.py"), case, "2"], capture_output=True, text=True,
-                       timeout=600, cwd=ROOT)
+    r = subprocess.run([sys.executable, str(ROOT / "tools" / "slab_check.py"), case, "2", mode], capture_output=True,
+                       text=True, timeout=600, cwd=ROOT)
     lines = [l for l in r.stdout.splitlines() if l.startswith("SLABCHECK ")]
     assert r.returncode == 0 and lines, r.stdout[-2000:] + r.stderr[-2000:]
     verdict = json.loads(lines[-1][len("SLABCHECK "):])
     assert verdict["bit_exact"] and verdict["absmax"] > 0, verdict
+    if mode == "native":
+        assert verdict["n_devices"] == 2 and verdict["halo_bytes"] > 0, verdict
+
+
+def test_executable_shards_over_visible_devices(built_lib, tmp_path):
+    """`fw25_engine` in a .dat directory with CUDA_VISIBLE_DEVICES=0,1 (what the reference launcher sets for
+    cuda_device_id=[0, 1], launcher.py:206) uses both GPUs and writes the same genout.dat as with one."""
+    if _n_gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    import os
+
+    import numpy as np
+
+    from fullwave25_b200.build import CLI
+    from tests.test_slab import _problem
+    pb = _problem("het3d")
+    outs = {}
+    for devs in ("0", "0,1"):
+        d = tmp_path / f"sim_{len(devs)}"
+        pb.to_dat_dir(d)
+        r = subprocess.run([str(CLI)], cwd=d, capture_output=True, text=True, timeout=600,
+                           env=dict(os.environ, CUDA_VISIBLE_DEVICES=devs))
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        assert f"{len(devs.split(','))} GPU(s)" in r.stdout
+        outs[devs] = np.fromfile(d / "genout.dat", np.float32)
+    assert np.abs(outs["0"]).max() > 0
+    np.testing.assert_array_equal(outs["0"], outs["0,1"])

@@ -21,21 +21,27 @@ from fullwave25_b200.slab import SlabDriver, partition
 from tests.test_slab import _problem
 
 
-def local_main(case, n):
-    """Single process, n devices: engine.run(pb, device_ids=[0..n-1]) == the reference's cuda_device_id list."""
-    from fullwave25_b200 import engine
+def local_main(case, n, mode="native"):
+    """Single process, n devices: engine.run(pb, device_ids=[0..n-1]) == the reference's cuda_device_id list.
+    mode "native": fw25_run's own multi-device runner (C++); "torch": the Python lockstep driver (runtime.run_local)."""
+    from fullwave25_b200 import engine, runtime
     from oracle import oracle
     pb = _problem(case)
-    got, stats = engine.run(pb, device_ids=tuple(range(n)))
+    if mode == "torch":
+        got, stats = runtime.run_local(pb, list(range(n)), return_stats=True)
+    else:
+        got, stats = engine.run(pb, device_ids=tuple(range(n)))
     want = oracle.run(pb)
-    print("SLABCHECK " + json.dumps({"case": case, "world": n, "mode": "in-process", "bit_exact": bool(np.array_equal(got, want)),
+    print("SLABCHECK " + json.dumps({"case": case, "world": n, "mode": "in-process " + mode,
+                                     "bit_exact": bool(np.array_equal(got, want)), "n_devices": int(stats.get("n_devices", 0)),
+                                     "halo_bytes": int(stats.get("halo_bytes", 0)),
                                      "absmax": float(np.abs(want).max()), "n_diff": int((got != want).sum())}), flush=True)
 
 
 def main():
     case = sys.argv[1] if len(sys.argv) > 1 else "het3d"
     if "RANK" not in os.environ:
-        return local_main(case, int(sys.argv[2]) if len(sys.argv) > 2 else 2)
+        return local_main(case, int(sys.argv[2]) if len(sys.argv) > 2 else 2, sys.argv[3] if len(sys.argv) > 3 else "native")
     rank, world, local = (int(os.environ[k]) for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
