@@ -365,7 +365,8 @@ struct Engine {
 
   bool use_ws() const { return ws != nullptr && (variant == 0 || variant == 3); }
   bool use_tiled() const { return plan != nullptr && variant != 1; }
-  bool use_2d() const { return p2d != nullptr && variant != 1; }
+  // variant 2 forces the tiled 2D sweeps; auto picks them for launches of >= ~0.8 M cells
+  bool use_2d(int rows) const { return p2d != nullptr && (variant == 2 || (variant == 0 && sweeps2d_worthwhile(G, rows))); }
 
   void clamp(int gx_lo, int gx_hi, int &a_lo, int &a_hi) const {
     a_lo = std::max(gx_lo - gx0, G.a_rim_lo);
@@ -377,23 +378,26 @@ struct Engine {
                   tt, d_air_idx, n_air, st);
     launches += launches_per_inject(n_src, n_air, tt, nTic, n_src_rim);
   }
-  void sweep_u(int gx_lo, int gx_hi, cudaStream_t st) {
+  // push (ws sweeps only): fused halo exchange, see HaloPush
+  void sweep_u(int gx_lo, int gx_hi, cudaStream_t st, const HaloPush *push = nullptr) {
     int a_lo, a_hi;
     clamp(gx_lo, gx_hi, a_lo, a_hi);
     if (a_hi <= a_lo) return;
-    if (use_ws()) { launches += launch_sweep_u_ws(ws, F, G, a_lo, a_hi, st); return; }
+    if (use_ws()) { launches += launch_sweep_u_ws(ws, F, G, a_lo, a_hi, st, push); return; }
+    if (push) fail(3, "fused halo push needs the warp-specialised sweeps");
     if (use_tiled()) { launches += launch_sweep_u_tiled(plan, F, G, a_lo, a_hi, st); return; }
-    if (use_2d()) { launches += launch_sweep_u_2d(p2d, F, G, a_lo, a_hi, st); return; }
+    if (use_2d(a_hi - a_lo)) { launches += launch_sweep_u_2d(p2d, F, G, a_lo, a_hi, st); return; }
     launch_sweep_u_simple(ndim, F, G, a_lo, a_hi, st);
     launches += (a_hi - a_lo + 32767) / 32768;
   }
-  void sweep_p(int gx_lo, int gx_hi, cudaStream_t st) {
+  void sweep_p(int gx_lo, int gx_hi, cudaStream_t st, const HaloPush *push = nullptr) {
     int a_lo, a_hi;
     clamp(gx_lo, gx_hi, a_lo, a_hi);
     if (a_hi <= a_lo) return;
-    if (use_ws()) { launches += launch_sweep_p_ws(ws, F, G, a_lo, a_hi, st); return; }
+    if (use_ws()) { launches += launch_sweep_p_ws(ws, F, G, a_lo, a_hi, st, push); return; }
+    if (push) fail(3, "fused halo push needs the warp-specialised sweeps");
     if (use_tiled()) { launches += launch_sweep_p_tiled(plan, F, G, a_lo, a_hi, st); return; }
-    if (use_2d()) { launches += launch_sweep_p_2d(p2d, F, G, a_lo, a_hi, st); return; }
+    if (use_2d(a_hi - a_lo)) { launches += launch_sweep_p_2d(p2d, F, G, a_lo, a_hi, st); return; }
     launch_sweep_p_simple(ndim, F, G, a_lo, a_hi, st);
     launches += (a_hi - a_lo + 32767) / 32768;
   }
@@ -518,6 +522,7 @@ struct fw25_engine {
 namespace {
 
 constexpr int M = fw25::M;
+using fw25::HaloPush;
 
 int n_frames_of(const fw25_problem *pb) {
   return pb->nT > 0 ? (pb->nT + pb->modT - 1) / std::max(pb->modT, 1) : 0;
@@ -557,6 +562,9 @@ struct MultiRun {
   std::vector<Dev> d;
   int t = 0;
   int64_t halo_bytes = 0;
+  // fused: the boundary sweeps store their results straight into the neighbour's ghost planes over NVLink
+  // (HaloPush) -- no copies.  Needs the warp-specialised 3D sweeps and peer access on every interface.
+  bool fused = false;
 
   ~MultiRun() {
     for (auto &x : d) {
@@ -605,16 +613,41 @@ struct MultiRun {
       for (cudaEvent_t *ev : {&x.ev_main, &x.ev_bu, &x.ev_bp, &x.ev_end, &x.ev_sent})
         FW_CUDA(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
     }
+    bool all_peer = true;
     for (int r = 0; r + 1 < n; ++r) {      // neighbours talk over NVLink when the platform allows it
       const int a = d[r].device, b = d[r + 1].device;
       int ab = 0, ba = 0;
-      if (a == b) continue;
+      if (a == b) continue;                // (tests: two slabs on one device)
       cudaDeviceCanAccessPeer(&ab, a, b);
       cudaDeviceCanAccessPeer(&ba, b, a);
       if (ab) { cudaSetDevice(a); cudaDeviceEnablePeerAccess(b, 0); }
       if (ba) { cudaSetDevice(b); cudaDeviceEnablePeerAccess(a, 0); }
       cudaGetLastError();                  // cudaErrorPeerAccessAlreadyEnabled is fine; copies are staged otherwise
+      all_peer = all_peer && ab && ba;
     }
+    fused = all_peer;
+    for (int r = 0; r < n; ++r) fused = fused && E(r).use_ws();
+    if (const char *ev = getenv("FW25_FUSED_HALO")) fused = fused && atoi(ev) != 0;
+  }
+
+  // what a boundary sweep of slab r next to neighbour `to` pushes: the neighbour's arrays, shifted so that r's
+  // element index lands on the same global plane; v, w only for the plane adjacent to the interface
+  HaloPush push_to(int r, int to, bool velocities) {
+    Engine &me = E(r), &nb = E(to);
+    const long long shift = (long long)(me.gx0 - nb.gx0) * me.G.sA;
+    HaloPush h{};
+    const int g8 = to < r ? d[r].own_lo : d[r].own_hi - M;       // the 8 planes next to the interface
+    h.lo0 = g8 - me.gx0;
+    h.hi0 = h.lo0 + M;
+    if (velocities) {
+      for (int k = 0; k < 3; ++k) h.a[k] = nb.F.q[k] + shift;
+      const int g1 = to < r ? d[r].own_lo : d[r].own_hi - 1;     // the one plane of v, w the neighbour reads
+      h.lo1 = g1 - me.gx0;
+      h.hi1 = h.lo1 + 1;
+    } else {
+      h.a[0] = nb.F.p + shift;
+    }
+    return h;
   }
 
   Engine &E(int r) { return d[r].h->e; }
@@ -635,6 +668,16 @@ struct MultiRun {
   // r's ghost planes are no longer being read
   void exchange(bool velocities) {
     const int n = (int)d.size();
+    if (fused) {                             // the boundary sweeps already pushed: only order the streams
+      for (int r = 0; r < n; ++r) {
+        Dev &x = d[r];
+        cudaEvent_t Dev::*done = velocities ? &Dev::ev_bu : &Dev::ev_bp;
+        FW_CUDA(cudaSetDevice(x.device));
+        if (x.has_lo) FW_CUDA(cudaStreamWaitEvent(x.bnd, d[r - 1].*done, 0));
+        if (x.has_hi) FW_CUDA(cudaStreamWaitEvent(x.bnd, d[r + 1].*done, 0));
+      }
+      return;
+    }
     for (int r = 0; r < n; ++r) {
       Dev &x = d[r];
       FW_CUDA(cudaSetDevice(x.device));
@@ -663,11 +706,20 @@ struct MultiRun {
     }
   }
 
-  template <class Fn>
-  void boundary(Dev &x, Fn &&fn) {
-    if (x.has_lo) fn(x.own_lo, std::min(x.own_lo + M, x.own_hi));
-    if (x.has_hi) fn(std::max(x.own_hi - M, x.own_lo), x.own_hi);
+  // Planes swept by a boundary launch: only the outer 8 cross the interface, but an 8-plane launch pays the
+  // x-marching kernels' chunk prologue for 8 planes of work, a full 32-plane chunk does not.
+  int bw(const Dev &x) const {
+    const int sides = (x.has_lo ? 1 : 0) + (x.has_hi ? 1 : 0);
+    return std::max(M, std::min(32, (x.own_hi - x.own_lo) / std::max(sides, 1)));
   }
+  template <class Fn>
+  void boundary(int r, Fn &&fn) {            // fn(lo, hi, neighbour)
+    Dev &x = d[r];
+    const int w = bw(x);
+    if (x.has_lo) fn(x.own_lo, std::min(x.own_lo + w, x.own_hi), r - 1);
+    if (x.has_hi) fn(std::max(x.own_hi - w, x.own_lo), x.own_hi, r + 1);
+  }
+  void plane_bytes(int r, int planes) { halo_bytes += (int64_t)planes * E(r).G.sA * (int64_t)sizeof(float); }
 
   void step() {
     const int n = (int)d.size();
@@ -679,7 +731,16 @@ struct MultiRun {
       e.inject(t, e.stream);
       FW_CUDA(cudaEventRecord(x.ev_main, e.stream));
       FW_CUDA(cudaStreamWaitEvent(x.bnd, x.ev_main, 0));
-      boundary(x, [&](int lo, int hi) { e.sweep_u(lo, hi, x.bnd); });
+      if (fused && t > 0) {                  // the neighbours' boundary fd_p of the previous step read their ghosts
+        if (x.has_lo) FW_CUDA(cudaStreamWaitEvent(x.bnd, d[r - 1].ev_bp, 0));
+        if (x.has_hi) FW_CUDA(cudaStreamWaitEvent(x.bnd, d[r + 1].ev_bp, 0));
+      }
+      boundary(r, [&](int lo, int hi, int to) {
+        if (!fused) { e.sweep_u(lo, hi, x.bnd); return; }
+        const HaloPush h = push_to(r, to, true);
+        e.sweep_u(lo, hi, x.bnd, &h);
+        plane_bytes(r, M + 2);
+      });
       FW_CUDA(cudaEventRecord(x.ev_bu, x.bnd));
     }
     exchange(true);
@@ -687,10 +748,15 @@ struct MultiRun {
       Dev &x = d[r];
       Engine &e = E(r);
       FW_CUDA(cudaSetDevice(x.device));
-      e.sweep_u(x.own_lo + (x.has_lo ? M : 0), x.own_hi - (x.has_hi ? M : 0), e.stream);
+      e.sweep_u(x.own_lo + (x.has_lo ? bw(x) : 0), x.own_hi - (x.has_hi ? bw(x) : 0), e.stream);
       FW_CUDA(cudaEventRecord(x.ev_main, e.stream));
       FW_CUDA(cudaStreamWaitEvent(x.bnd, x.ev_main, 0));
-      boundary(x, [&](int lo, int hi) { e.sweep_p(lo, hi, x.bnd); });
+      boundary(r, [&](int lo, int hi, int to) {   // (fused: exchange(true) made this stream wait for the
+        if (!fused) { e.sweep_p(lo, hi, x.bnd); return; }   //  neighbours' boundary fd_u, the last readers of their p ghosts)
+        const HaloPush h = push_to(r, to, false);
+        e.sweep_p(lo, hi, x.bnd, &h);
+        plane_bytes(r, M);
+      });
       FW_CUDA(cudaEventRecord(x.ev_bp, x.bnd));
     }
     exchange(false);
@@ -700,7 +766,7 @@ struct MultiRun {
       FW_CUDA(cudaSetDevice(x.device));
       FW_CUDA(cudaEventRecord(x.ev_end, x.bnd));
       FW_CUDA(cudaStreamWaitEvent(e.stream, x.ev_bu, 0));     // interior fd_p reads the boundary planes' velocities
-      e.sweep_p(x.own_lo + (x.has_lo ? M : 0), x.own_hi - (x.has_hi ? M : 0), e.stream);
+      e.sweep_p(x.own_lo + (x.has_lo ? bw(x) : 0), x.own_hi - (x.has_hi ? bw(x) : 0), e.stream);
       if (t % e.modT == 0) {
         FW_CUDA(cudaStreamWaitEvent(e.stream, x.ev_bp, 0));
         e.record(t / e.modT, e.stream);

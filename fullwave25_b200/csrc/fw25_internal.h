@@ -23,12 +23,16 @@ struct WsPlan;
 bool ws_supported(int ndim, const Geom &G);
 WsPlan *ws_plan_create(const Fields &F, const Geom &G, const float *host_dmap, cudaStream_t st, std::string *err);
 void ws_plan_destroy(WsPlan *pl);
-int launch_sweep_u_ws(const WsPlan *pl, const Fields &F, const Geom &G, int a_lo, int a_hi, cudaStream_t st);
-int launch_sweep_p_ws(const WsPlan *pl, const Fields &F, const Geom &G, int a_lo, int a_hi, cudaStream_t st);
+// push != nullptr: fused halo exchange -- the launch also stores its results into the neighbour's ghost planes
+int launch_sweep_u_ws(const WsPlan *pl, const Fields &F, const Geom &G, int a_lo, int a_hi, cudaStream_t st,
+                      const HaloPush *push = nullptr);
+int launch_sweep_p_ws(const WsPlan *pl, const Fields &F, const Geom &G, int a_lo, int a_hi, cudaStream_t st,
+                      const HaloPush *push = nullptr);
 
 // TMA-tiled 2D sweeps: fw25_sweeps_2d.cu
 struct Plan2D;
 bool sweeps2d_supported(int ndim, const Geom &G);
+bool sweeps2d_worthwhile(const Geom &G, int rows);   // auto mode: tiled only where it beats the simple sweeps
 Plan2D *plan2d_create(const Fields &F, const Geom &G, const float *host_dmap, cudaStream_t st, std::string *err);
 void plan2d_destroy(Plan2D *pl);
 int launch_sweep_u_2d(const Plan2D *pl, const Fields &F, const Geom &G, int a_lo, int a_hi, cudaStream_t st);

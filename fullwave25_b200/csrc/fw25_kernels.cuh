@@ -55,4 +55,13 @@ struct Geom {
   int a_rim_lo, a_rim_hi; // local A range that may be updated: global [8, nXglobal-8) ∩ owned
 };
 
+// Fused halo exchange (boundary sweeps of an x-slab): peer-mapped state arrays of the neighbour GPU, pre-offset
+// so that THIS engine's element index addresses the same global plane there.  fd_u: a[0..2] = u, v, w; fd_p:
+// a[0] = p.  a[0] is pushed for local planes [lo0, hi0) (the 8 planes next to the interface), v and w only for
+// [lo1, hi1) (the one plane the cross terms read); the launch itself may cover more planes.
+struct HaloPush {
+  float *a[3];
+  int lo0, hi0, lo1, hi1;
+};
+
 }  // namespace fw25

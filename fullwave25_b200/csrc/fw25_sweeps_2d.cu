@@ -267,20 +267,32 @@ bool tmap2d(CUtensorMap *m, const void *base, const Geom &G, int box_c, int box_
 
 }  // namespace
 
+constexpr int kRpt[4] = {1, 2, 4, 8};    // rows per CTA the kernels are instantiated for
+static int rpt_slot(int rpt) { return rpt == 1 ? 0 : rpt == 2 ? 1 : rpt == 4 ? 2 : 3; }
+
 struct Plan2D {
   StencilTab2 *tab = nullptr;
-  CUtensorMap p[2], u[2], v[2];   // [0]: RPT = 4, [1]: RPT = 8
+  CUtensorMap p[4], u[4], v[4];   // one set of boxes per entry of kRpt
 };
 
 bool sweeps2d_supported(int ndim, const Geom &G) {
   return ndim == 2 && G.nB == 1 && G.pitch % 32 == 0 && G.nC > 2 * M && encode_fn_2d() != nullptr;
 }
 
+// Below ~0.8 M cells per launch the one-thread-per-cell kernels win: such a grid is L2-resident and has too few
+// cells to keep 148 SMs busy with 4 cells per thread (B200, profiles/sweep_2d_r01.txt: 0.52 M cells 21.6 vs 17.7
+// Gpt/s, 1.05 M cells 24.0 vs 27.0, 3.2 M cells 23.6 vs 30.2).  FW25_2D_MIN_CELLS overrides the threshold.
+bool sweeps2d_worthwhile(const Geom &G, int rows) {
+  const char *ev = getenv("FW25_2D_MIN_CELLS");
+  const long long thr = ev ? atoll(ev) : 786432;
+  return (long long)rows * G.nC >= thr;
+}
+
 Plan2D *plan2d_create(const Fields &F, const Geom &G, const float *host_dmap, cudaStream_t st, std::string *err) {
   auto *pl = new Plan2D();
   bool ok = true;
-  for (int v = 0; v < 2 && ok; ++v) {
-    const int rpt = v ? 8 : 4;
+  for (int v = 0; v < 4 && ok; ++v) {
+    const int rpt = kRpt[v];
     ok = tmap2d(&pl->p[v], F.p, G, TC2 + 16, rpt + 15, err) && tmap2d(&pl->u[v], F.q[0], G, TC2 + 8, rpt + 15, err) &&
          tmap2d(&pl->v[v], F.q[2], G, TC2 + 16, rpt + 2, err);
   }
@@ -315,7 +327,7 @@ void plan2d_destroy(Plan2D *pl) {
 static int pick_rpt(const Geom &G, int rows) {
   const char *ev = getenv("FW25_2D_RPT");
   const int env = ev ? atoi(ev) : 0;
-  if (env == 4 || env == 8) return env;
+  if (env == 1 || env == 2 || env == 4 || env == 8) return env;
   const long long ctas8 = (long long)((G.nC - M + TC2 - 1) / TC2) * ((rows + 7) / 8);
   return ctas8 >= 148LL * FW25_WS_2D_MINB * 2 ? 8 : 4;
 }
@@ -324,8 +336,11 @@ int launch_sweep_u_2d(const Plan2D *pl, const Fields &F, const Geom &G, int a_lo
   if (a_hi <= a_lo) return 0;
   const int rpt = pick_rpt(G, a_hi - a_lo);
   dim3 grd((G.nC - M + TC2 - 1) / TC2, (a_hi - a_lo + rpt - 1) / rpt, 1);
-  if (rpt == 8) k_sweep_u_2d<8><<<grd, TC2, 0, st>>>(pl->p[1], F, G, pl->tab, a_lo, a_hi);
-  else k_sweep_u_2d<4><<<grd, TC2, 0, st>>>(pl->p[0], F, G, pl->tab, a_lo, a_hi);
+  const CUtensorMap &mp = pl->p[rpt_slot(rpt)];
+  if (rpt == 8) k_sweep_u_2d<8><<<grd, TC2, 0, st>>>(mp, F, G, pl->tab, a_lo, a_hi);
+  else if (rpt == 4) k_sweep_u_2d<4><<<grd, TC2, 0, st>>>(mp, F, G, pl->tab, a_lo, a_hi);
+  else if (rpt == 2) k_sweep_u_2d<2><<<grd, TC2, 0, st>>>(mp, F, G, pl->tab, a_lo, a_hi);
+  else k_sweep_u_2d<1><<<grd, TC2, 0, st>>>(mp, F, G, pl->tab, a_lo, a_hi);
   return 1;
 }
 
@@ -333,8 +348,11 @@ int launch_sweep_p_2d(const Plan2D *pl, const Fields &F, const Geom &G, int a_lo
   if (a_hi <= a_lo) return 0;
   const int rpt = pick_rpt(G, a_hi - a_lo);
   dim3 grd((G.nC - M + TC2 - 1) / TC2, (a_hi - a_lo + rpt - 1) / rpt, 1);
-  if (rpt == 8) k_sweep_p_2d<8><<<grd, TC2, 0, st>>>(pl->u[1], pl->v[1], F, G, pl->tab, a_lo, a_hi);
-  else k_sweep_p_2d<4><<<grd, TC2, 0, st>>>(pl->u[0], pl->v[0], F, G, pl->tab, a_lo, a_hi);
+  const CUtensorMap &mu = pl->u[rpt_slot(rpt)], &mv = pl->v[rpt_slot(rpt)];
+  if (rpt == 8) k_sweep_p_2d<8><<<grd, TC2, 0, st>>>(mu, mv, F, G, pl->tab, a_lo, a_hi);
+  else if (rpt == 4) k_sweep_p_2d<4><<<grd, TC2, 0, st>>>(mu, mv, F, G, pl->tab, a_lo, a_hi);
+  else if (rpt == 2) k_sweep_p_2d<2><<<grd, TC2, 0, st>>>(mu, mv, F, G, pl->tab, a_lo, a_hi);
+  else k_sweep_p_2d<1><<<grd, TC2, 0, st>>>(mu, mv, F, G, pl->tab, a_lo, a_hi);
   return 1;
 }
 

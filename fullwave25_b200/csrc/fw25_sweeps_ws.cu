@@ -84,10 +84,13 @@ struct alignas(128) SmemP {
 };
 
 // ------------------------------------------------------------------------------------------ fd_u
-template <int TY, int MINB>
+// PUSH: the launch covers the planes next to an x-slab interface and also stores its results into the neighbour
+// GPU's ghost planes through a peer-mapped pointer (NVLink): the halo exchange is part of the sweep, tile by
+// tile, instead of a copy after it (u: every plane of the launch; v, w: only the plane the cross terms read).
+template <int TY, int MINB, bool PUSH>
 __global__ void __launch_bounds__((TY + 1) * TZ, MINB)
     k_sweep_u_ws(const CUtensorMap *__restrict__ maps, const Fields F, const Geom G,
-                 const StencilTab *__restrict__ tab, int a_lo, int a_hi, int Lx, int hint) {
+                 const StencilTab *__restrict__ tab, int a_lo, int a_hi, int Lx, int hint, const HaloPush push) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SmemU<TY> &S = *reinterpret_cast<SmemU<TY> *>(smem_raw);
   constexpr int HY = TY + 2 * M, HZ = TZ + 2 * M;
@@ -234,6 +237,10 @@ FW25_UNROLL_X(FW25_WS_UNROLL)
       __stcs(F.psi[1][0] + gi, m10); __stcs(F.psi[1][1] + gi, m11);
       __stcs(F.psi[2][0] + gi, m20); __stcs(F.psi[2][1] + gi, m21);
       __stcs(F.q[0] + gi, q0); __stcs(F.q[1] + gi, q1); __stcs(F.q[2] + gi, q2);
+      if constexpr (PUSH) {
+        if (xa + n >= push.lo0 && xa + n < push.hi0) push.a[0][gi] = q0;
+        if (xa + n >= push.lo1 && xa + n < push.hi1) { push.a[1][gi] = q1; push.a[2][gi] = q2; }
+      }
 #pragma unroll
       for (int j = 0; j < 15; ++j) pc[j] = pc[j + 1];
     }
@@ -246,10 +253,10 @@ FW25_UNROLL_X(FW25_WS_UNROLL)
 }
 
 // ------------------------------------------------------------------------------------------ fd_p
-template <int TY, int MINB>
+template <int TY, int MINB, bool PUSH>
 __global__ void __launch_bounds__((TY + 1) * TZ, MINB)
     k_sweep_p_ws(const CUtensorMap *__restrict__ maps, const Fields F, const Geom G,
-                 const StencilTab *__restrict__ tab, int a_lo, int a_hi, int Lx, int hint) {
+                 const StencilTab *__restrict__ tab, int a_lo, int a_hi, int Lx, int hint, const HaloPush push) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SmemP<TY> &S = *reinterpret_cast<SmemP<TY> *>(smem_raw);
   constexpr uint32_t U_BYTES = (TY + 2) * (TZ + 8) * 4, V_BYTES = (TY + 2 * M) * (TZ + 8) * 4,
@@ -387,7 +394,11 @@ FW25_UNROLL_X(FW25_WS_UNROLL)
       __stcs(F.phi[0][0] + gi, f00); __stcs(F.phi[0][1] + gi, f01);
       __stcs(F.phi[1][0] + gi, f10); __stcs(F.phi[1][1] + gi, f11);
       __stcs(F.phi[2][0] + gi, f20); __stcs(F.phi[2][1] + gi, f21);
-      F.p[gi] = fma_(-At, Bt, pc);   // p is the next sweep's stencil field: default caching
+      const float pn = fma_(-At, Bt, pc);
+      F.p[gi] = pn;                  // p is the next sweep's stencil field: default caching
+      if constexpr (PUSH) {
+        if (xa + n >= push.lo0 && xa + n < push.hi0) push.a[0][gi] = pn;
+      }
 #pragma unroll
       for (int j = 0; j < 15; ++j) uc[j] = uc[j + 1];
     }
@@ -505,9 +516,13 @@ WsPlan *ws_plan_create(const Fields &F, const Geom &G, const float *host_dmap, c
       cudaMemcpyAsync(pl->maps, h.data(), sizeof(CUtensorMap) * MP_END, cudaMemcpyHostToDevice, st) != cudaSuccess ||
       cudaMemcpyAsync(pl->tab, t.data(), sizeof(StencilTab) * nd, cudaMemcpyHostToDevice, st) != cudaSuccess ||
       cudaStreamSynchronize(st) != cudaSuccess ||
-      cudaFuncSetAttribute(k_sweep_u_ws<TY_WS, MINB_WS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      cudaFuncSetAttribute(k_sweep_u_ws<TY_WS, MINB_WS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)sizeof(SmemU<TY_WS>)) != cudaSuccess ||
-      cudaFuncSetAttribute(k_sweep_p_ws<TY_WS, MINB_WS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      cudaFuncSetAttribute(k_sweep_p_ws<TY_WS, MINB_WS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)sizeof(SmemP<TY_WS>)) != cudaSuccess ||
+      cudaFuncSetAttribute(k_sweep_u_ws<TY_WS, MINB_WS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)sizeof(SmemU<TY_WS>)) != cudaSuccess ||
+      cudaFuncSetAttribute(k_sweep_p_ws<TY_WS, MINB_WS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)sizeof(SmemP<TY_WS>)) != cudaSuccess) {
     *err = std::string("warp-specialised plan: ") + cudaGetErrorString(cudaGetLastError());
     if (pl->maps) cudaFree(pl->maps);
@@ -525,21 +540,33 @@ void ws_plan_destroy(WsPlan *pl) {
   delete pl;
 }
 
-int launch_sweep_u_ws(const WsPlan *pl, const Fields &F, const Geom &G, int a_lo, int a_hi, cudaStream_t st) {
+int launch_sweep_u_ws(const WsPlan *pl, const Fields &F, const Geom &G, int a_lo, int a_hi, cudaStream_t st,
+                      const HaloPush *push) {
   if (a_hi <= a_lo) return 0;
   const int Lx = pick_chunk_ws(G, a_hi - a_lo);
   dim3 blk(TZ, TY_WS + 1, 1);
   dim3 grd((G.nC - M + TZ - 1) / TZ, (G.nB - 2 * M + TY_WS - 1) / TY_WS, (a_hi - a_lo + Lx - 1) / Lx);
-  k_sweep_u_ws<TY_WS, MINB_WS><<<grd, blk, sizeof(SmemU<TY_WS>), st>>>(pl->maps, F, G, pl->tab, a_lo, a_hi, Lx, ws_hint());
+  if (push)
+    k_sweep_u_ws<TY_WS, MINB_WS, true><<<grd, blk, sizeof(SmemU<TY_WS>), st>>>(pl->maps, F, G, pl->tab, a_lo, a_hi, Lx,
+                                                                                ws_hint(), *push);
+  else
+    k_sweep_u_ws<TY_WS, MINB_WS, false><<<grd, blk, sizeof(SmemU<TY_WS>), st>>>(pl->maps, F, G, pl->tab, a_lo, a_hi, Lx,
+                                                                                 ws_hint(), HaloPush{});
   return 1;
 }
 
-int launch_sweep_p_ws(const WsPlan *pl, const Fields &F, const Geom &G, int a_lo, int a_hi, cudaStream_t st) {
+int launch_sweep_p_ws(const WsPlan *pl, const Fields &F, const Geom &G, int a_lo, int a_hi, cudaStream_t st,
+                      const HaloPush *push) {
   if (a_hi <= a_lo) return 0;
   const int Lx = pick_chunk_ws(G, a_hi - a_lo);
   dim3 blk(TZ, TY_WS + 1, 1);
   dim3 grd((G.nC - M + TZ - 1) / TZ, (G.nB - 2 * M + TY_WS - 1) / TY_WS, (a_hi - a_lo + Lx - 1) / Lx);
-  k_sweep_p_ws<TY_WS, MINB_WS><<<grd, blk, sizeof(SmemP<TY_WS>), st>>>(pl->maps, F, G, pl->tab, a_lo, a_hi, Lx, ws_hint());
+  if (push)
+    k_sweep_p_ws<TY_WS, MINB_WS, true><<<grd, blk, sizeof(SmemP<TY_WS>), st>>>(pl->maps, F, G, pl->tab, a_lo, a_hi, Lx,
+                                                                                ws_hint(), *push);
+  else
+    k_sweep_p_ws<TY_WS, MINB_WS, false><<<grd, blk, sizeof(SmemP<TY_WS>), st>>>(pl->maps, F, G, pl->tab, a_lo, a_hi, Lx,
+                                                                                 ws_hint(), HaloPush{});
   return 1;
 }
 
