@@ -83,9 +83,36 @@ int main() {
   const size_t n = (size_t)pb.nX * pb.nY * pb.nZ;
   const char *names[13] = {"rho", "K", "beta", "kappax", "kappau", "apmlx1", "bpmlx1", "apmlx2", "bpmlx2",
                            "apmlu1", "bpmlu1", "apmlu2", "bpmlu2"};
+  // kappay.dat present: the anisotropic file set (input_file_writer.py:592-620) -- per-axis maps
+  const bool aniso = file_exists("kappay.dat");
   std::vector<float> maps[13];
   for (int i = 0; i < 13; ++i)
     if (!read_all(std::string(names[i]) + ".dat", maps[i], n)) return 2;
+  std::vector<std::vector<float>> amaps;
+  fw25_aniso an;
+  memset(&an, 0, sizeof an);
+  if (aniso) {
+    const char *vel = "xyz";
+    const char *prs = pb.ndim == 2 ? "uw" : "uvw";
+    amaps.reserve(60);
+    auto load = [&](const std::string &stem) -> const float * {
+      amaps.emplace_back();
+      if (!read_all(stem + ".dat", amaps.back(), n)) return nullptr;
+      return amaps.back().data();
+    };
+    bool ok2 = true;
+    for (int ax = 0; ax < pb.ndim && ok2; ++ax) {
+      const std::string v(1, vel[ax]), q(1, prs[ax]);
+      ok2 = (an.kappa_vel[ax] = load("kappa" + v)) && (an.kappa_prs[ax] = load("kappa" + q));
+      for (int nu = 0; nu < 2 && ok2; ++nu) {
+        const std::string k = std::to_string(nu + 1);
+        ok2 = (an.a_vel[ax][nu] = load("apml" + v + k)) && (an.b_vel[ax][nu] = load("bpml" + v + k)) &&
+              (an.a_prs[ax][nu] = load("apml" + q + k)) && (an.b_prs[ax][nu] = load("bpml" + q + k));
+      }
+    }
+    if (!ok2) return 2;
+    pb.aniso = &an;
+  }
   std::vector<float> dmap, icmat;
   std::vector<int32_t> dcmap, icc, outc, icczero;
   if (!read_all("dmap.dat", dmap, (size_t)18 * pb.ndmap) || !read_all("dcmap.dat", dcmap, n) ||

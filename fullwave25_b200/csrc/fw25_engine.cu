@@ -76,6 +76,8 @@ struct Engine {
   int64_t launches = 0;
   int variant = 0;
   int64_t h2d_bytes = 0;
+  bool aniso = false;            // per-axis relaxation maps that really differ: ANISO simple sweeps only
+  bool aniso_protocol = false;   // the problem came as the anisotropic file set (its binaries ignore air voxels)
 
   // Whole steps replayed from a CUDA graph (small grids are launch-bound: the 2D examples step in ~10 us).  The step
   // number then lives on the device (*d_t, advanced by the graph's last node) so that one instantiated graph
@@ -243,20 +245,65 @@ struct Engine {
     const bool dev_maps = pb.maps_on_device != 0;
     const int mp = pb.map_pitch > 0 ? pb.map_pitch : G.nC;
     if (mp < G.nC) fail(1, "map_pitch is smaller than the fastest axis");
-    const float *maps[13] = {pb.rho, pb.K, pb.beta, pb.kappax, pb.kappau, pb.apmlx1, pb.bpmlx1,
-                             pb.apmlx2, pb.bpmlx2, pb.apmlu1, pb.bpmlu1, pb.apmlu2, pb.bpmlu2};
+    // anisotropic file set: per-axis maps.  When every axis holds the same values (what the reference's Python
+    // layer writes) the isotropic kernels run on the x-axis copy; otherwise the ANISO simple sweeps read all of them.
+    const fw25_aniso *an = pb.aniso;
+    aniso_protocol = an != nullptr;
+    if (an) {
+      for (int ax = 0; ax < ndim; ++ax) {
+        bool ok = an->kappa_vel[ax] && an->kappa_prs[ax];
+        for (int nu = 0; nu < 2; ++nu)
+          ok = ok && an->a_vel[ax][nu] && an->b_vel[ax][nu] && an->a_prs[ax][nu] && an->b_prs[ax][nu];
+        if (!ok) fail(1, "an anisotropic map pointer is NULL");
+      }
+      aniso = dev_maps;                      // device maps are not compared
+      if (!dev_maps) {
+        const size_t bytes = (size_t)nXl * nY * nZ * sizeof(float);
+        auto same = [&](const float *a, const float *b) { return a == b || memcmp(a, b, bytes) == 0; };
+        for (int ax = 1; ax < ndim && !aniso; ++ax) {
+          aniso = !same(an->kappa_vel[ax], an->kappa_vel[0]) || !same(an->kappa_prs[ax], an->kappa_prs[0]);
+          for (int nu = 0; nu < 2 && !aniso; ++nu)
+            aniso = !same(an->a_vel[ax][nu], an->a_vel[0][nu]) || !same(an->b_vel[ax][nu], an->b_vel[0][nu]) ||
+                    !same(an->a_prs[ax][nu], an->a_prs[0][nu]) || !same(an->b_prs[ax][nu], an->b_prs[0][nu]);
+        }
+      }
+    }
+    const float *maps[13] = {pb.rho, pb.K, pb.beta,
+                             an ? an->kappa_vel[0] : pb.kappax, an ? an->kappa_prs[0] : pb.kappau,
+                             an ? an->a_vel[0][0] : pb.apmlx1, an ? an->b_vel[0][0] : pb.bpmlx1,
+                             an ? an->a_vel[0][1] : pb.apmlx2, an ? an->b_vel[0][1] : pb.bpmlx2,
+                             an ? an->a_prs[0][0] : pb.apmlu1, an ? an->b_prs[0][0] : pb.bpmlu1,
+                             an ? an->a_prs[0][1] : pb.apmlu2, an ? an->b_prs[0][1] : pb.bpmlu2};
     for (auto m : maps)
       if (!m) fail(1, "a medium map pointer is NULL");
     if (!pb.dmap || !pb.dcmap) fail(1, "dmap / dcmap pointer is NULL");
-    F.rho = upload_map(pb.rho, dev_maps, mp);
-    F.K = upload_map(pb.K, dev_maps, mp);
-    F.beta = upload_map(pb.beta, dev_maps, mp);
-    F.kappax = upload_map(pb.kappax, dev_maps, mp);
-    F.kappau = upload_map(pb.kappau, dev_maps, mp);
-    F.ax1 = upload_map(pb.apmlx1, dev_maps, mp); F.bx1 = upload_map(pb.bpmlx1, dev_maps, mp);
-    F.ax2 = upload_map(pb.apmlx2, dev_maps, mp); F.bx2 = upload_map(pb.bpmlx2, dev_maps, mp);
-    F.au1 = upload_map(pb.apmlu1, dev_maps, mp); F.bu1 = upload_map(pb.bpmlu1, dev_maps, mp);
-    F.au2 = upload_map(pb.apmlu2, dev_maps, mp); F.bu2 = upload_map(pb.bpmlu2, dev_maps, mp);
+    F.rho = upload_map(maps[0], dev_maps, mp);
+    F.K = upload_map(maps[1], dev_maps, mp);
+    F.beta = upload_map(maps[2], dev_maps, mp);
+    F.kappax = upload_map(maps[3], dev_maps, mp);
+    F.kappau = upload_map(maps[4], dev_maps, mp);
+    F.ax1 = upload_map(maps[5], dev_maps, mp); F.bx1 = upload_map(maps[6], dev_maps, mp);
+    F.ax2 = upload_map(maps[7], dev_maps, mp); F.bx2 = upload_map(maps[8], dev_maps, mp);
+    F.au1 = upload_map(maps[9], dev_maps, mp); F.bu1 = upload_map(maps[10], dev_maps, mp);
+    F.au2 = upload_map(maps[11], dev_maps, mp); F.bu2 = upload_map(maps[12], dev_maps, mp);
+    for (int slot = 0; slot < 3; ++slot) {   // per-axis slots: alias the per-sweep maps unless truly anisotropic
+      F.kv[slot] = F.kappax; F.kp[slot] = F.kappau;
+      F.av[slot][0] = F.ax1; F.bv[slot][0] = F.bx1; F.av[slot][1] = F.ax2; F.bv[slot][1] = F.bx2;
+      F.ap[slot][0] = F.au1; F.bp[slot][0] = F.bu1; F.ap[slot][1] = F.au2; F.bp[slot][1] = F.bu2;
+    }
+    if (aniso) {
+      for (int ax = 1; ax < ndim; ++ax) {
+        const int slot = (ndim == 2) ? 2 : ax;   // 2D: the reference's y is the engine's contiguous axis C
+        F.kv[slot] = upload_map(an->kappa_vel[ax], dev_maps, mp);
+        F.kp[slot] = upload_map(an->kappa_prs[ax], dev_maps, mp);
+        for (int nu = 0; nu < 2; ++nu) {
+          F.av[slot][nu] = upload_map(an->a_vel[ax][nu], dev_maps, mp);
+          F.bv[slot][nu] = upload_map(an->b_vel[ax][nu], dev_maps, mp);
+          F.ap[slot][nu] = upload_map(an->a_prs[ax][nu], dev_maps, mp);
+          F.bp[slot][nu] = upload_map(an->b_prs[ax][nu], dev_maps, mp);
+        }
+      }
+    }
     {
       // Reference 3D behaviour: only the first nX*nY entries of dcmap are honoured (fw25.h, dcmap_full3d).
       const bool mask = ndim == 3 && !pb.dcmap_full3d;
@@ -291,7 +338,7 @@ struct Engine {
         F.phi[ax][nu] = used ? state(nullptr) : nullptr;
       }
 
-    if (tiled_supported(ndim, G)) {
+    if (!aniso && tiled_supported(ndim, G)) {
       std::string perr;
       std::vector<float> hd((size_t)18 * pb.ndmap);
       memcpy(hd.data(), pb.dmap, hd.size() * 4);
@@ -303,7 +350,7 @@ struct Engine {
       }
     }
 
-    if (sweeps2d_supported(ndim, G)) {
+    if (!aniso && sweeps2d_supported(ndim, G)) {
       std::string perr;
       std::vector<float> hd((size_t)18 * pb.ndmap);
       memcpy(hd.data(), pb.dmap, hd.size() * 4);
@@ -316,7 +363,7 @@ struct Engine {
     {  // air voxels (ghost planes included)
       std::vector<long long> idx;
       if (pb.ncoordszero > 0 && !pb.icczero) fail(1, "icczero pointer is NULL");
-      for (int i = 0; i < pb.ncoordszero; ++i) {
+      for (int i = 0; i < (aniso_protocol ? 0 : pb.ncoordszero); ++i) {   // (the anisotropic binaries have no air kernel)
         const int32_t *c = pb.icczero + (size_t)i * nd;
         if (!coord_ok(c)) fail(1, "icczero: air coordinate outside the grid");
         if (c[0] < gx0 || c[0] >= gx0 + nXl) continue;
@@ -387,7 +434,7 @@ struct Engine {
     if (push) fail(3, "fused halo push needs the warp-specialised sweeps");
     if (use_tiled()) { launches += launch_sweep_u_tiled(plan, F, G, a_lo, a_hi, st); return; }
     if (use_2d(a_hi - a_lo)) { launches += launch_sweep_u_2d(p2d, F, G, a_lo, a_hi, st); return; }
-    launch_sweep_u_simple(ndim, F, G, a_lo, a_hi, st);
+    launch_sweep_u_simple(ndim, F, G, a_lo, a_hi, st, aniso);
     launches += (a_hi - a_lo + 32767) / 32768;
   }
   void sweep_p(int gx_lo, int gx_hi, cudaStream_t st, const HaloPush *push = nullptr) {
@@ -398,7 +445,7 @@ struct Engine {
     if (push) fail(3, "fused halo push needs the warp-specialised sweeps");
     if (use_tiled()) { launches += launch_sweep_p_tiled(plan, F, G, a_lo, a_hi, st); return; }
     if (use_2d(a_hi - a_lo)) { launches += launch_sweep_p_2d(p2d, F, G, a_lo, a_hi, st); return; }
-    launch_sweep_p_simple(ndim, F, G, a_lo, a_hi, st);
+    launch_sweep_p_simple(ndim, F, G, a_lo, a_hi, st, aniso);
     launches += (a_hi - a_lo + 32767) / 32768;
   }
   void record(int frame, cudaStream_t st) {
@@ -557,7 +604,7 @@ struct MultiRun {
     int own_lo = 0, own_hi = 0, gx0 = 0, gx1 = 0;
     bool has_lo = false, has_hi = false;
     cudaStream_t bnd = nullptr;
-    cudaEvent_t ev_main = nullptr, ev_bu = nullptr, ev_bp = nullptr, ev_end = nullptr, ev_sent = nullptr;
+    cudaEvent_t ev_main = nullptr, ev_bu = nullptr, ev_bp = nullptr, ev_end = nullptr, ev_sent = nullptr, ev_in = nullptr;
   };
   std::vector<Dev> d;
   int t = 0;
@@ -565,13 +612,17 @@ struct MultiRun {
   // fused: the boundary sweeps store their results straight into the neighbour's ghost planes over NVLink
   // (HaloPush) -- no copies.  Needs the warp-specialised 3D sweeps and peer access on every interface.
   bool fused = false;
+  // concurrent (default): boundary sweeps on the high-priority stream next to the interior sweep.  serial
+  // (FW25_SLAB_SCHEDULE=serial): boundary planes first on the engine's own stream, then the interior -- one sweep
+  // kernel on the GPU at a time; only copies use the boundary stream.  Measured equal on a B200 pair.
+  bool serial = false;
 
   ~MultiRun() {
     for (auto &x : d) {
       cudaSetDevice(x.device);
       if (x.h) cudaStreamSynchronize(x.h->e.stream);
       if (x.bnd) { cudaStreamSynchronize(x.bnd); cudaStreamDestroy(x.bnd); }
-      for (cudaEvent_t ev : {x.ev_main, x.ev_bu, x.ev_bp, x.ev_end, x.ev_sent})
+      for (cudaEvent_t ev : {x.ev_main, x.ev_bu, x.ev_bp, x.ev_end, x.ev_sent, x.ev_in})
         if (ev) cudaEventDestroy(ev);
       if (x.h) fw25_destroy(x.h);
     }
@@ -603,6 +654,21 @@ struct MultiRun {
       for (auto m : maps)
         if (*m) *m += off;
       if (sub.dcmap) sub.dcmap += off;
+      fw25_aniso an_sub;
+      if (pb.aniso) {
+        an_sub = *pb.aniso;
+        for (int ax = 0; ax < 3; ++ax) {
+          if (an_sub.kappa_vel[ax]) an_sub.kappa_vel[ax] += off;
+          if (an_sub.kappa_prs[ax]) an_sub.kappa_prs[ax] += off;
+          for (int nu = 0; nu < 2; ++nu) {
+            if (an_sub.a_vel[ax][nu]) an_sub.a_vel[ax][nu] += off;
+            if (an_sub.b_vel[ax][nu]) an_sub.b_vel[ax][nu] += off;
+            if (an_sub.a_prs[ax][nu]) an_sub.a_prs[ax][nu] += off;
+            if (an_sub.b_prs[ax][nu]) an_sub.b_prs[ax][nu] += off;
+          }
+        }
+        sub.aniso = &an_sub;
+      }
       fw25_slab sl{nX, x.gx0, x.own_lo, x.own_hi};
       const int rc = fw25_create(&sub, &sl, x.device, &x.h);
       if (rc) throw Fail{rc};
@@ -610,7 +676,7 @@ struct MultiRun {
       int lo_pri = 0, hi_pri = 0;
       FW_CUDA(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
       FW_CUDA(cudaStreamCreateWithPriority(&x.bnd, cudaStreamNonBlocking, hi_pri));
-      for (cudaEvent_t *ev : {&x.ev_main, &x.ev_bu, &x.ev_bp, &x.ev_end, &x.ev_sent})
+      for (cudaEvent_t *ev : {&x.ev_main, &x.ev_bu, &x.ev_bp, &x.ev_end, &x.ev_sent, &x.ev_in})
         FW_CUDA(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
     }
     bool all_peer = true;
@@ -628,6 +694,7 @@ struct MultiRun {
     fused = all_peer;
     for (int r = 0; r < n; ++r) fused = fused && E(r).use_ws();
     if (const char *ev = getenv("FW25_FUSED_HALO")) fused = fused && atoi(ev) != 0;
+    if (const char *ev = getenv("FW25_SLAB_SCHEDULE")) serial = std::string(ev) == "serial";
   }
 
   // what a boundary sweep of slab r next to neighbour `to` pushes: the neighbour's arrays, shifted so that r's
@@ -721,7 +788,92 @@ struct MultiRun {
   }
   void plane_bytes(int r, int planes) { halo_bytes += (int64_t)planes * E(r).G.sA * (int64_t)sizeof(float); }
 
+  void wait_neighbours(cudaStream_t st, int r, cudaEvent_t Dev::*ev) {
+    if (d[r].has_lo) FW_CUDA(cudaStreamWaitEvent(st, d[r - 1].*ev, 0));
+    if (d[r].has_hi) FW_CUDA(cudaStreamWaitEvent(st, d[r + 1].*ev, 0));
+  }
+  // copies of one exchange on the boundary streams; `done` is recorded on each boundary stream once the planes of
+  // both neighbours have landed.  final_ev: the sender's planes are final AND (the same event of the neighbour) the
+  // neighbour's ghost planes are no longer read.
+  void copy_exchange(bool velocities, cudaEvent_t Dev::*final_ev, cudaEvent_t Dev::*done) {
+    const int n = (int)d.size();
+    for (int r = 0; r < n; ++r) {
+      Dev &x = d[r];
+      FW_CUDA(cudaSetDevice(x.device));
+      FW_CUDA(cudaStreamWaitEvent(x.bnd, x.*final_ev, 0));
+      const int nd = E(r).ndim;
+      for (int side = 0; side < 2; ++side) {
+        if (side == 0 ? !x.has_lo : !x.has_hi) continue;
+        const int to = side == 0 ? r - 1 : r + 1;
+        FW_CUDA(cudaStreamWaitEvent(x.bnd, d[to].*final_ev, 0));
+        auto lo_of = [&](int w) { return side == 0 ? x.own_lo : x.own_hi - w; };
+        if (velocities) {
+          send_planes(r, to, 0, lo_of(M), M);
+          if (nd == 3) send_planes(r, to, 1, lo_of(1), 1);
+          send_planes(r, to, 2, lo_of(1), 1);
+        } else {
+          send_planes(r, to, -1, lo_of(M), M);
+        }
+      }
+      FW_CUDA(cudaEventRecord(x.ev_sent, x.bnd));
+    }
+    for (int r = 0; r < n; ++r) {
+      Dev &x = d[r];
+      FW_CUDA(cudaSetDevice(x.device));
+      wait_neighbours(x.bnd, r, &Dev::ev_sent);
+      FW_CUDA(cudaEventRecord(x.*done, x.bnd));
+    }
+  }
+
+  void step_serial() {
+    const int n = (int)d.size();
+    for (int r = 0; r < n; ++r) {          // inject, boundary planes of fd_u
+      Dev &x = d[r];
+      Engine &e = E(r);
+      FW_CUDA(cudaSetDevice(x.device));
+      if (t > 0) {                         // my ghost p planes are in; the neighbours' ghost velocities were read
+        if (fused) wait_neighbours(e.stream, r, &Dev::ev_bp);
+        else FW_CUDA(cudaStreamWaitEvent(e.stream, x.ev_end, 0));
+      }
+      e.inject(t, e.stream);
+      boundary(r, [&](int lo, int hi, int to) {
+        if (!fused) { e.sweep_u(lo, hi, e.stream); return; }
+        const HaloPush h = push_to(r, to, true);
+        e.sweep_u(lo, hi, e.stream, &h);
+        plane_bytes(r, M + 2);
+      });
+      FW_CUDA(cudaEventRecord(x.ev_bu, e.stream));
+    }
+    if (!fused) copy_exchange(true, &Dev::ev_bu, &Dev::ev_in);
+    for (int r = 0; r < n; ++r) {          // interior fd_u (the transfers overlap it), boundary planes of fd_p
+      Dev &x = d[r];
+      Engine &e = E(r);
+      FW_CUDA(cudaSetDevice(x.device));
+      e.sweep_u(x.own_lo + (x.has_lo ? bw(x) : 0), x.own_hi - (x.has_hi ? bw(x) : 0), e.stream);
+      if (fused) wait_neighbours(e.stream, r, &Dev::ev_bu);     // pushed velocities landed; their p ghosts were read
+      else FW_CUDA(cudaStreamWaitEvent(e.stream, x.ev_in, 0));
+      boundary(r, [&](int lo, int hi, int to) {
+        if (!fused) { e.sweep_p(lo, hi, e.stream); return; }
+        const HaloPush h = push_to(r, to, false);
+        e.sweep_p(lo, hi, e.stream, &h);
+        plane_bytes(r, M);
+      });
+      FW_CUDA(cudaEventRecord(x.ev_bp, e.stream));
+    }
+    if (!fused) copy_exchange(false, &Dev::ev_bp, &Dev::ev_end);
+    for (int r = 0; r < n; ++r) {          // interior fd_p (the p transfers overlap it), sensors
+      Dev &x = d[r];
+      Engine &e = E(r);
+      FW_CUDA(cudaSetDevice(x.device));
+      e.sweep_p(x.own_lo + (x.has_lo ? bw(x) : 0), x.own_hi - (x.has_hi ? bw(x) : 0), e.stream);
+      if (t % e.modT == 0) e.record(t / e.modT, e.stream);
+      e.t = t + 1;
+    }
+    ++t;
+  }
+
   void step() {
+    if (serial) { step_serial(); return; }
     const int n = (int)d.size();
     for (int r = 0; r < n; ++r) {          // inject, boundary planes of fd_u first
       Dev &x = d[r];

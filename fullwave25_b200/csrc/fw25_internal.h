@@ -7,8 +7,9 @@
 namespace fw25 {
 
 // simple (L1/L2-cached) sweeps: fw25_sweeps_simple.cu.  a_lo/a_hi are LOCAL plane indices.
-void launch_sweep_u_simple(int ndim, const Fields &F, const Geom &G, int a_lo, int a_hi, cudaStream_t st);
-void launch_sweep_p_simple(int ndim, const Fields &F, const Geom &G, int a_lo, int a_hi, cudaStream_t st);
+// aniso: read the per-axis maps (Fields::kv .. bp) instead of the per-sweep ones
+void launch_sweep_u_simple(int ndim, const Fields &F, const Geom &G, int a_lo, int a_hi, cudaStream_t st, bool aniso = false);
+void launch_sweep_p_simple(int ndim, const Fields &F, const Geom &G, int a_lo, int a_hi, cudaStream_t st, bool aniso = false);
 
 // TMA-tiled x-marching sweeps (3D): fw25_sweeps_tiled.cu.  Return the number of kernels launched.
 struct TiledPlan;

@@ -39,6 +39,9 @@ struct Fields {
   const float *au1, *bu1, *au2, *bu2;  // apmlu*/bpmlu*: pressure sweep
   const int32_t *dcmap;
   const float *dmap;                   // [9][2][ndmap]
+  // anisotropic file set (per axis A,B,C; nu): only read by the ANISO instantiations of the simple sweeps
+  const float *kv[3], *av[3][2], *bv[3][2];   // velocity sweep
+  const float *kp[3], *ap[3][2], *bp[3][2];   // pressure sweep
   // state
   float *p;
   float *q[3];                         // velocity along A,B,C

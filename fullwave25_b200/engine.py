@@ -24,6 +24,12 @@ class EngineError(RuntimeError):
     """The native engine reported a failure (non-zero return code + fw25_last_error())."""
 
 
+class CAniso(C.Structure):
+    """fw25_aniso: per-axis maps of the anisotropic file set; [axis] or [axis][nu]."""
+    _fields_ = [("kappa_vel", C.c_void_p * 3), ("a_vel", (C.c_void_p * 2) * 3), ("b_vel", (C.c_void_p * 2) * 3),
+                ("kappa_prs", C.c_void_p * 3), ("a_prs", (C.c_void_p * 2) * 3), ("b_prs", (C.c_void_p * 2) * 3)]
+
+
 class CProblem(C.Structure):
     _fields_ = [
         ("ndim", C.c_int32), ("nX", C.c_int32), ("nY", C.c_int32), ("nZ", C.c_int32),
@@ -39,6 +45,7 @@ class CProblem(C.Structure):
         ("ncoordszero", C.c_int32), ("icczero", C.c_void_p),
         ("maps_on_device", C.c_int32), ("map_pitch", C.c_int32), ("dcmap_full3d", C.c_int32),
         ("ext_p", C.c_void_p), ("ext_u", C.c_void_p), ("ext_v", C.c_void_p), ("ext_w", C.c_void_p),
+        ("aniso", C.POINTER(CAniso)),
     ]
 
 
@@ -139,6 +146,22 @@ def marshal(pb: Problem, *, device_maps: dict | None = None, ext_state: dict | N
     if ext_state:
         s.ext_p, s.ext_u = ext_state.get("p"), ext_state.get("u")
         s.ext_v, s.ext_w = ext_state.get("v"), ext_state.get("w")
+    if pb.aniso is not None:
+        if device_maps is not None:
+            raise EngineError("device-resident maps are isotropic only")
+        an = CAniso()
+        vel = ("x", "y", "z")[: pb.ndim]
+        prs = ("u", "w") if pb.ndim == 2 else ("u", "v", "w")
+        for ax in range(pb.ndim):
+            an.kappa_vel[ax] = pb.aniso["kappa" + vel[ax]].ctypes.data
+            an.kappa_prs[ax] = pb.aniso["kappa" + prs[ax]].ctypes.data
+            for nu in range(2):
+                an.a_vel[ax][nu] = pb.aniso[f"apml{vel[ax]}{nu + 1}"].ctypes.data
+                an.b_vel[ax][nu] = pb.aniso[f"bpml{vel[ax]}{nu + 1}"].ctypes.data
+                an.a_prs[ax][nu] = pb.aniso[f"apml{prs[ax]}{nu + 1}"].ctypes.data
+                an.b_prs[ax][nu] = pb.aniso[f"bpml{prs[ax]}{nu + 1}"].ctypes.data
+        keep.append(an)
+        s.aniso = C.pointer(an)
     return s, keep
 
 

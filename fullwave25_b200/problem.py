@@ -63,6 +63,10 @@ class Problem:
     # False = the reference 3D binary's behaviour: only the first nX*nY entries of dcmap are honoured, the
     # rest read 0 (include/fw25.h, fw25_problem.dcmap_full3d).  No effect in 2D.
     dcmap_full3d: bool = False
+    # Anisotropic-relaxation protocol (use_isotropic_relaxation=False upstream; input_file_writer.py:592-620):
+    # {file stem: map} for kappa{x,y[,z]}, kappa{u,w[,v]}, apml/bpml{x,y[,z],u,w[,v]}{1,2}.  None = isotropic.
+    # When set, the isotropic fields kappax .. bpmlu2 above hold the x-axis members (kappax, kappau, apmlx*, apmlu*).
+    aniso: dict | None = None
 
     # ------------------------------------------------------------------ basics
     @property
@@ -89,12 +93,28 @@ class Problem:
     def n_frames(self) -> int:
         return -(-self.nT // self.modT) if self.nT > 0 else 0
 
+    @staticmethod
+    def aniso_stems(ndim: int) -> tuple[str, ...]:
+        """File stems of the anisotropic protocol, per-axis letters: velocity sweep x, y[, z]; pressure sweep
+        u, w (2D) / u, v, w (3D) for axes x, y[, z]."""
+        letters = ("x", "y", "u", "w") if ndim == 2 else ("x", "y", "z", "u", "v", "w")
+        return tuple(f"kappa{l}" for l in letters) + tuple(f"{ab}pml{l}{nu}" for l in letters for nu in (1, 2)
+                                                           for ab in ("a", "b"))
+
     def normalise(self) -> "Problem":
         """Cast every array to the protocol dtype / shape (C-contiguous) and validate sizes."""
         if self.ndim not in (2, 3):
             raise ValueError("ndim must be 2 or 3")
         if self.ndim == 2:
             self.nZ = 1
+        if self.aniso is not None:
+            for stem in self.aniso_stems(self.ndim):
+                if stem not in self.aniso:
+                    raise ValueError(f"anisotropic problem lacks {stem}")
+                a = np.ascontiguousarray(self.aniso[stem], dtype=np.float32)
+                if a.size != self.n_points:
+                    raise ValueError(f"{stem}: {a.size} values, grid has {self.n_points}")
+                self.aniso[stem] = a.reshape(self.shape)
         for name in MAP_NAMES:
             a = np.ascontiguousarray(getattr(self, name), dtype=np.float32)
             if a.size != self.n_points:
@@ -161,6 +181,9 @@ class Problem:
             return np.fromfile(f, dtype=np.int32)[: cnt * ndim].reshape(cnt, ndim)
 
         maps = {name: fmap(name) for name in MAP_NAMES}
+        aniso = None
+        if (d / "kappay.dat").exists():      # the anisotropic file set (dangling static-map links do not count)
+            aniso = {stem: fmap(stem) for stem in cls.aniso_stems(ndim)}
         pb = cls(
             ndim=ndim, nX=nX, nY=nY, nZ=nZ, nT=i32("nT"), nTic=nTic, modT=i32("modT"), ndmap=ndmap,
             dX=f32("dX"), dT=f32("dT"), **maps,
@@ -170,6 +193,7 @@ class Problem:
             icmat=np.fromfile(d / "icmat.dat", dtype=np.float32)[: ncoords * nTic].reshape(ncoords, nTic),
             outc=coords("outc", ncoordsout),
             icczero=coords("icczero", ncoordszero),
+            aniso=aniso,
         )
         return pb.normalise()
 
@@ -180,6 +204,8 @@ class Problem:
         d.mkdir(parents=True, exist_ok=True)
         for name in MAP_NAMES:
             getattr(self, name).astype(np.float32).tofile(d / f"{name}.dat")
+        for stem, a in (self.aniso or {}).items():
+            a.astype(np.float32).tofile(d / f"{stem}.dat")
         ex = self.extra
         np.asarray(ex.get("c", np.zeros(self.shape, np.float32)), dtype=np.float32).tofile(d / "c.dat")
         np.asarray(ex.get("d", np.zeros((9, 2))), dtype=np.float32).tofile(d / "d.dat")
@@ -234,6 +260,8 @@ class Problem:
     def slab(self, gx0: int, gx1: int) -> "Problem":
         """Planes [gx0, gx1) of every grid array (views); coordinates stay global."""
         kw = {name: getattr(self, name)[gx0:gx1] for name in MAP_NAMES}
+        if self.aniso is not None:
+            kw["aniso"] = {k: v[gx0:gx1] for k, v in self.aniso.items()}
         return Problem(ndim=self.ndim, nX=gx1 - gx0, nY=self.nY, nZ=self.nZ, nT=self.nT, nTic=self.nTic,
                        modT=self.modT, ndmap=self.ndmap, dX=self.dX, dT=self.dT, **kw, dmap=self.dmap,
                        dcmap=self.dcmap[gx0:gx1], icc=self.icc, icmat=self.icmat, outc=self.outc,

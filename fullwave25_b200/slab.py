@@ -87,12 +87,12 @@ class SlabDriver:
         self.t = 0
         self.exchange_enabled = True      # False: skip the transfers (to expose the halo cost; results invalid)
         self._ev_end = None
-        # "serial": boundary planes first ON THE MAIN STREAM, then the interior; only the transfers run on the
-        # boundary stream.  "concurrent": boundary sweeps on the high-priority stream next to the interior sweep.
-        # Serial keeps one sweep kernel on the GPU at a time, like a single-GPU run (concurrent sweeps disturb each
-        # other's L2 wavefront: N = 2 bench 45.3 ms/step against 43.3 on one GPU with the transfers fully hidden).
+        # "concurrent" (default): boundary sweeps on the high-priority stream next to the interior sweep.
+        # "serial": boundary planes first ON THE MAIN STREAM, then the interior; only the transfers use the boundary
+        # stream (one sweep kernel on the GPU at a time, like a single-GPU run).  Measured equal on a B200 pair
+        # (800x1240x1240 per GPU: 45.14 vs 45.38 ms/step, profiles/README.md), so the simpler overlap stays.
         import os
-        self.schedule = os.environ.get("FW25_SLAB_SCHEDULE", "serial")
+        self.schedule = os.environ.get("FW25_SLAB_SCHEDULE", "concurrent")
 
     # plane ranges -------------------------------------------------------------------------------
     def _boundary_width(self):

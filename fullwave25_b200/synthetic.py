@@ -82,7 +82,7 @@ def tone_burst(nt: int, dt: float, f0: float, n_cycles: float = 2.0, amp: float 
 def make_problem(shape, *, nT: int, f0: float = 1e6, c0: float = 1540.0, ppw: int = 12, cfl: float = 0.2,
                  n_pml: int = 6, n_trans: int = 4, block: int = 5, seed: int = 1234, modT: int = 1,
                  n_sensors: int = 64, n_air: int = 8, homogeneous: bool = False,
-                 source_layers: int = 3, amp: float = 1e5) -> Problem:
+                 source_layers: int = 3, amp: float = 1e5, aniso: bool = False) -> Problem:
     """shape: EXTENDED grid (nX, nY[, nZ]) including the boundary layer of M + n_pml + n_trans cells."""
     shape = tuple(int(s) for s in shape)
     ndim = len(shape)
@@ -131,6 +131,32 @@ def make_problem(shape, *, nT: int, f0: float = 1e6, c0: float = 1540.0, ppw: in
         maps[f"apml{tag}1"], maps[f"bpml{tag}1"] = a1, b1
         maps[f"apml{tag}2"], maps[f"bpml{tag}2"] = a2, b2
 
+    aniso_maps = None
+    if aniso:
+        # anisotropic protocol: one kappa / a / b set PER AXIS.  Each axis gets its own PML ramp (along that axis
+        # only, a split-field layer) and slightly different relaxation strengths, so that every array differs from
+        # every other one everywhere -- a permuted axis assignment cannot go unnoticed.
+        aniso_maps = {}
+        letters = {0: ("x", "y", "z")[:ndim], 1: ("u", "w") if ndim == 2 else ("u", "v", "w")}
+        for fam in (0, 1):
+            for ax, letter in enumerate(letters[fam]):
+                sh = [1] * ndim
+                sh[ax] = shape[ax]
+                xi_a = np.broadcast_to(prof[ax][0].reshape(sh), shape)
+                tr_a = np.broadcast_to(prof[ax][1].reshape(sh), shape)
+                kappa = (1.0 + (table[fam, lab, 0] - 1.0) * (1 - tr_a)) * (1.0 + 0.003 * ax)
+                d1 = table[fam, lab, 1] * (1 - tr_a) * (1.0 + 0.15 * ax) + d_pml * xi_a**2
+                al1 = table[fam, lab, 2] * (1 - tr_a)
+                d2 = table[fam, lab, 3] * (1 - tr_a) * (1.0 - 0.1 * ax)
+                al2 = table[fam, lab, 4] * (1 - tr_a)
+                a1, b1 = calc_a_b(d1, kappa, al1, dt)
+                a2, b2 = calc_a_b(d2, kappa, al2, dt)
+                aniso_maps[f"kappa{letter}"] = kappa
+                aniso_maps[f"apml{letter}1"], aniso_maps[f"bpml{letter}1"] = a1, b1
+                aniso_maps[f"apml{letter}2"], aniso_maps[f"bpml{letter}2"] = a2, b2
+        for k in list(maps):                       # the isotropic slots hold the x-axis members
+            maps[k] = aniso_maps[k]
+
     d_tab, dmap, dcmap, ndmap = stencil.tables(c, dt=dt, dx=dx, cfl=cfl, is_3d=ndim == 3)
 
     # plane source: `source_layers` planes at x = nb .. nb+layers-1 over the user cross-section
@@ -160,6 +186,6 @@ def make_problem(shape, *, nT: int, f0: float = 1e6, c0: float = 1540.0, ppw: in
         ndim=ndim, nX=shape[0], nY=shape[1], nZ=shape[2] if ndim == 3 else 1, nT=nT, nTic=nTic, modT=modT,
         ndmap=ndmap, dX=float(np.float32(dx)), dT=float(np.float32(dt)), rho=rho, K=K, beta=beta, **maps,
         dmap=dmap, dcmap=dcmap, icc=icc, icmat=icmat, outc=outc, icczero=icczero,
-        extra={"c": c, "d": d_tab, "c0": c0, "dY": dx, "dZ": dx},
+        extra={"c": c, "d": d_tab, "c0": c0, "dY": dx, "dZ": dx}, aniso=aniso_maps,
     )
     return pb.normalise()

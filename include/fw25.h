@@ -23,8 +23,18 @@
 extern "C" {
 #endif
 
-#define FW25_ABI_VERSION 3
+#define FW25_ABI_VERSION 4
 #define FW25_M 8 /* stencil half-width: solver.py:296 (m_spatial_order = 8), kernels launched with M = 8 */
+
+/* Anisotropic-relaxation file set (upstream `use_isotropic_relaxation=False`, input_file_writer.py:592-620; engine
+ * family fullwave2_{2d,3d}_2_relax_multi_gpu_*): the same update with one kappa / a / b map PER AXIS.  Index 0, 1, 2 =
+ * axis x, y, z (2D: 0, 1); [nu] = relaxation mechanism 1, 2.  Velocity sweep (fd_u): files kappa{x,y,z}.dat,
+ * apml{x,y,z}{1,2}.dat, bpml{x,y,z}{1,2}.dat.  Pressure sweep (fd_p): kappa{u,w}.dat (2D: axes x, y) or
+ * kappa{u,v,w}.dat (3D: axes x, y, z), apml/bpml likewise.  Same layout and residency rules as the isotropic maps. */
+typedef struct fw25_aniso {
+  const float *kappa_vel[3], *a_vel[3][2], *b_vel[3][2];
+  const float *kappa_prs[3], *a_prs[3][2], *b_prs[3][2];
+} fw25_aniso;
 
 /* One simulation = the contents of one reference "simulation_dir".
  * Field names are the reference's .dat file stems (input_file_writer.py:766-821, :581-627). */
@@ -61,6 +71,11 @@ typedef struct fw25_problem {
   float *ext_p, *ext_u, *ext_v, *ext_w; /* optional caller-owned DEVICE state arrays [nX][nY][pitch]
                                  (pitch = fw25_pitch(nZ)); lets a multi-process driver hand the halo
                                  planes to NCCL without a copy.  NULL: the engine allocates. */
+  const fw25_aniso *aniso;    /* NULL: isotropic file set (above).  Else the per-axis maps; kappax .. bpmlu2 above are
+                                 ignored, and -- like the reference's anisotropic binaries, which have no
+                                 inject_source_zero kernel -- so are the air voxels (icczero).  When every axis holds
+                                 identical values (what the reference's own Python layer writes, pml_builder.py:
+                                 896-1005) the engine runs its isotropic kernels on one copy. */
 } fw25_problem;
 
 /* x-slab owned by one engine when the grid is sharded along x (the reference's slab partitioner,

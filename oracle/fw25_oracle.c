@@ -20,6 +20,31 @@
 #define M 8
 
 
+/* per-axis coefficient arrays of one sweep: the isotropic binaries use the same array on every axis */
+typedef struct {
+  const float *k[3], *a[3][2], *b[3][2];
+} axis_coef;
+
+static axis_coef coef_vel(const fw25o_problem *pb) {
+  axis_coef c;
+  for (int ax = 0; ax < 3; ++ax) {
+    c.k[ax] = pb->aniso ? pb->kappa_vel[ax] : pb->kappax;
+    c.a[ax][0] = pb->aniso ? pb->a_vel[ax][0] : pb->apmlx1; c.b[ax][0] = pb->aniso ? pb->b_vel[ax][0] : pb->bpmlx1;
+    c.a[ax][1] = pb->aniso ? pb->a_vel[ax][1] : pb->apmlx2; c.b[ax][1] = pb->aniso ? pb->b_vel[ax][1] : pb->bpmlx2;
+  }
+  return c;
+}
+
+static axis_coef coef_prs(const fw25o_problem *pb) {
+  axis_coef c;
+  for (int ax = 0; ax < 3; ++ax) {
+    c.k[ax] = pb->aniso ? pb->kappa_prs[ax] : pb->kappau;
+    c.a[ax][0] = pb->aniso ? pb->a_prs[ax][0] : pb->apmlu1; c.b[ax][0] = pb->aniso ? pb->b_prs[ax][0] : pb->bpmlu1;
+    c.a[ax][1] = pb->aniso ? pb->a_prs[ax][1] : pb->apmlu2; c.b[ax][1] = pb->aniso ? pb->b_prs[ax][1] : pb->bpmlu2;
+  }
+  return c;
+}
+
 static inline int in_rim(const fw25o_problem *pb, int x, int y, int z) {
   if (x < M || x >= pb->nX - M) return 1;
   if (y < M || y >= pb->nY - M) return 1;
@@ -69,6 +94,7 @@ static void sweep_u_3d(const fw25o_problem *pb, fw25o_state *st, int x_lo, int x
   const ptrdiff_t sY = nZ, sX = (ptrdiff_t)nY * nZ;
   const float dX = pb->dX, dT = pb->dT;
   const float *restrict p = st->p;
+  const axis_coef C = coef_vel(pb);
   if (x_lo < M) x_lo = M;
   if (x_hi > nX - M) x_hi = nX - M;
 #pragma omp parallel for collapse(2) schedule(static)
@@ -101,23 +127,21 @@ static void sweep_u_3d(const fw25o_problem *pb, fw25o_state *st, int x_lo, int x
         gx = fmaf(E, cx, gx) / dX; /* PTX L548-550 */
         gy = fmaf(E, cy, gy) / dX;
         gz = fmaf(E, cz, gz) / dX;
-        const float a1 = pb->apmlx1[i], b1 = pb->bpmlx1[i], a2 = pb->apmlx2[i], b2 = pb->bpmlx2[i];
         /* PTX L551-608: psi' = fma(b, psi, g*a) */
-        const float px1 = fmaf(b1, st->psi[0][i], gx * a1);
-        const float px2 = fmaf(b2, st->psi[3][i], gx * a2);
-        const float py1 = fmaf(b1, st->psi[1][i], gy * a1);
-        const float py2 = fmaf(b2, st->psi[4][i], gy * a2);
-        const float pz1 = fmaf(b1, st->psi[2][i], gz * a1);
-        const float pz2 = fmaf(b2, st->psi[5][i], gz * a2);
+        const float px1 = fmaf(C.b[0][0][i], st->psi[0][i], gx * C.a[0][0][i]);
+        const float px2 = fmaf(C.b[0][1][i], st->psi[3][i], gx * C.a[0][1][i]);
+        const float py1 = fmaf(C.b[1][0][i], st->psi[1][i], gy * C.a[1][0][i]);
+        const float py2 = fmaf(C.b[1][1][i], st->psi[4][i], gy * C.a[1][1][i]);
+        const float pz1 = fmaf(C.b[2][0][i], st->psi[2][i], gz * C.a[2][0][i]);
+        const float pz2 = fmaf(C.b[2][1][i], st->psi[5][i], gz * C.a[2][1][i]);
         st->psi[0][i] = px1; st->psi[3][i] = px2;
         st->psi[1][i] = py1; st->psi[4][i] = py2;
         st->psi[2][i] = pz1; st->psi[5][i] = pz2;
         /* PTX L609-671 + SASS: s = (dT/rho) / fma(rcp(K), p, 1); q' = FFMA(-(s), t, q) */
         const float s = (dT / pb->rho[i]) / fmaf(1.0f / pb->K[i], p[i], 1.0f);
-        const float kx = pb->kappax[i];
-        st->u[i] = fmaf(-s, (gx / kx + px1) + px2, st->u[i]);
-        st->v[i] = fmaf(-s, (gy / kx + py1) + py2, st->v[i]);
-        st->w[i] = fmaf(-s, (gz / kx + pz1) + pz2, st->w[i]);
+        st->u[i] = fmaf(-s, (gx / C.k[0][i] + px1) + px2, st->u[i]);
+        st->v[i] = fmaf(-s, (gy / C.k[1][i] + py1) + py2, st->v[i]);
+        st->w[i] = fmaf(-s, (gz / C.k[2][i] + pz1) + pz2, st->w[i]);
       }
 }
 
@@ -127,6 +151,7 @@ static void sweep_p_3d(const fw25o_problem *pb, fw25o_state *st, int x_lo, int x
   const ptrdiff_t sY = nZ, sX = (ptrdiff_t)nY * nZ;
   const float dX = pb->dX, dT = pb->dT;
   const float *restrict u = st->u, *restrict v = st->v, *restrict w = st->w;
+  const axis_coef C = coef_prs(pb);
   if (x_lo < M) x_lo = M;
   if (x_hi > nX - M) x_hi = nX - M;
 #pragma omp parallel for collapse(2) schedule(static)
@@ -159,20 +184,19 @@ static void sweep_p_3d(const fw25o_problem *pb, fw25o_state *st, int x_lo, int x
         hx = fmaf(E, cu, hx) / dX;
         hy = fmaf(E, cv, hy) / dX;
         hz = fmaf(E, cw, hz) / dX;
-        const float a1 = pb->apmlu1[i], b1 = pb->bpmlu1[i], a2 = pb->apmlu2[i], b2 = pb->bpmlu2[i];
-        const float fx1 = fmaf(b1, st->phi[0][i], hx * a1);
-        const float fx2 = fmaf(b2, st->phi[3][i], hx * a2);
-        const float fy1 = fmaf(b1, st->phi[1][i], hy * a1);
-        const float fy2 = fmaf(b2, st->phi[4][i], hy * a2);
-        const float fz1 = fmaf(b1, st->phi[2][i], hz * a1);
-        const float fz2 = fmaf(b2, st->phi[5][i], hz * a2);
+        const float fx1 = fmaf(C.b[0][0][i], st->phi[0][i], hx * C.a[0][0][i]);
+        const float fx2 = fmaf(C.b[0][1][i], st->phi[3][i], hx * C.a[0][1][i]);
+        const float fy1 = fmaf(C.b[1][0][i], st->phi[1][i], hy * C.a[1][0][i]);
+        const float fy2 = fmaf(C.b[1][1][i], st->phi[4][i], hy * C.a[1][1][i]);
+        const float fz1 = fmaf(C.b[2][0][i], st->phi[2][i], hz * C.a[2][0][i]);
+        const float fz2 = fmaf(C.b[2][1][i], st->phi[5][i], hz * C.a[2][1][i]);
         st->phi[0][i] = fx1; st->phi[3][i] = fx2;
         st->phi[1][i] = fy1; st->phi[4][i] = fy2;
         st->phi[2][i] = fz1; st->phi[5][i] = fz2;
         /* PTX L1286-1319 + SASS tail */
-        const float Kc = pb->K[i], ku = pb->kappau[i], bt = pb->beta[i], pc = st->p[i];
-        float S = hx / ku + hy / ku;
-        S = hz / ku + S;
+        const float Kc = pb->K[i], bt = pb->beta[i], pc = st->p[i];
+        float S = hx / C.k[0][i] + hy / C.k[1][i];
+        S = hz / C.k[2][i] + S;
         S = fx1 + S; S = fx2 + S; S = fy1 + S; S = fy2 + S; S = fz1 + S; S = fz2 + S;
         const float A = (dT * Kc) * S;
         const float B = fmaf(pc, (1.0f / Kc) * (1.0f - (bt + bt)), 1.0f);
@@ -188,6 +212,7 @@ static void sweep_u_2d(const fw25o_problem *pb, fw25o_state *st, int x_lo, int x
   const ptrdiff_t sX = nY;
   const float dX = pb->dX, dT = pb->dT;
   const float *restrict p = st->p;
+  const axis_coef C = coef_vel(pb);
   if (x_lo < M) x_lo = M;
   if (x_hi > nX - M) x_hi = nX - M;
 #pragma omp parallel for schedule(static)
@@ -208,17 +233,15 @@ static void sweep_u_2d(const fw25o_problem *pb, fw25o_state *st, int x_lo, int x
       cy = cy + p[i - sX + 1]; cy = cy - p[i - sX];
       gx = fmaf(E, cx, gx) / dX;
       gy = fmaf(E, cy, gy) / dX;
-      const float a1 = pb->apmlx1[i], b1 = pb->bpmlx1[i], a2 = pb->apmlx2[i], b2 = pb->bpmlx2[i];
-      const float px1 = fmaf(b1, st->psi[0][i], gx * a1);
-      const float px2 = fmaf(b2, st->psi[3][i], gx * a2);
-      const float py1 = fmaf(b1, st->psi[1][i], gy * a1);
-      const float py2 = fmaf(b2, st->psi[4][i], gy * a2);
+      const float px1 = fmaf(C.b[0][0][i], st->psi[0][i], gx * C.a[0][0][i]);
+      const float px2 = fmaf(C.b[0][1][i], st->psi[3][i], gx * C.a[0][1][i]);
+      const float py1 = fmaf(C.b[1][0][i], st->psi[1][i], gy * C.a[1][0][i]);
+      const float py2 = fmaf(C.b[1][1][i], st->psi[4][i], gy * C.a[1][1][i]);
       st->psi[0][i] = px1; st->psi[3][i] = px2;
       st->psi[1][i] = py1; st->psi[4][i] = py2;
       const float s = (dT / pb->rho[i]) / fmaf(1.0f / pb->K[i], p[i], 1.0f);
-      const float kx = pb->kappax[i];
-      st->u[i] = fmaf(-s, (gx / kx + px1) + px2, st->u[i]);
-      st->v[i] = fmaf(-s, (gy / kx + py1) + py2, st->v[i]);
+      st->u[i] = fmaf(-s, (gx / C.k[0][i] + px1) + px2, st->u[i]);
+      st->v[i] = fmaf(-s, (gy / C.k[1][i] + py1) + py2, st->v[i]);
     }
 }
 
@@ -228,6 +251,7 @@ static void sweep_p_2d(const fw25o_problem *pb, fw25o_state *st, int x_lo, int x
   const ptrdiff_t sX = nY;
   const float dX = pb->dX, dT = pb->dT;
   const float *restrict u = st->u, *restrict v = st->v;
+  const axis_coef C = coef_prs(pb);
   if (x_lo < M) x_lo = M;
   if (x_hi > nX - M) x_hi = nX - M;
 #pragma omp parallel for schedule(static)
@@ -248,15 +272,14 @@ static void sweep_p_2d(const fw25o_problem *pb, fw25o_state *st, int x_lo, int x
       cv = cv + v[i - sX]; cv = cv - v[i - sX - 1];
       hx = fmaf(E, cu, hx) / dX;
       hy = fmaf(E, cv, hy) / dX;
-      const float a1 = pb->apmlu1[i], b1 = pb->bpmlu1[i], a2 = pb->apmlu2[i], b2 = pb->bpmlu2[i];
-      const float fx1 = fmaf(b1, st->phi[0][i], hx * a1);
-      const float fx2 = fmaf(b2, st->phi[3][i], hx * a2);
-      const float fy1 = fmaf(b1, st->phi[1][i], hy * a1);
-      const float fy2 = fmaf(b2, st->phi[4][i], hy * a2);
+      const float fx1 = fmaf(C.b[0][0][i], st->phi[0][i], hx * C.a[0][0][i]);
+      const float fx2 = fmaf(C.b[0][1][i], st->phi[3][i], hx * C.a[0][1][i]);
+      const float fy1 = fmaf(C.b[1][0][i], st->phi[1][i], hy * C.a[1][0][i]);
+      const float fy2 = fmaf(C.b[1][1][i], st->phi[4][i], hy * C.a[1][1][i]);
       st->phi[0][i] = fx1; st->phi[3][i] = fx2;
       st->phi[1][i] = fy1; st->phi[4][i] = fy2;
-      const float Kc = pb->K[i], ku = pb->kappau[i], bt = pb->beta[i], pc = st->p[i];
-      float S = hx / ku + hy / ku;
+      const float Kc = pb->K[i], bt = pb->beta[i], pc = st->p[i];
+      float S = hx / C.k[0][i] + hy / C.k[1][i];
       S = fx1 + S; S = fx2 + S; S = fy1 + S; S = fy2 + S;
       const float A = (dT * Kc) * S;
       const float B = fmaf(pc, (1.0f / Kc) * (1.0f - (bt + bt)), 1.0f);

@@ -51,6 +51,14 @@ typedef struct fw25o_problem {
   int32_t dcmap_full3d;      /* 0: the 3D binary's behaviour (only the first nX*nY dcmap entries are
                                 loaded, the rest read 0 -- see dcmap_3d in fw25_oracle.c); 1: per-voxel */
   int32_t nX_dcmap;          /* nX of the WHOLE grid for that rule (== nX unless pb is a slab view) */
+  /* Anisotropic-relaxation binaries (fullwave2_{2d,3d}_2_relax_multi_gpu_*; 2D PTX L38-934, 3D PTX L38-1427 of
+   * those files): the same arithmetic with one kappa / a / b array PER AXIS instead of one per sweep.
+   * aniso != 0: the velocity sweep uses kappa_vel[axis], a_vel[axis][nu], b_vel[axis][nu] (files kappa{x,y,z},
+   * apml{x,y,z}{1,2}, bpml{x,y,z}{1,2}) and the pressure sweep kappa_prs / a_prs / b_prs (files kappa{u,..},
+   * apml{u,..}{1,2}; 2D: u, w for axes x, y; 3D: u, v, w for x, y, z); the isotropic fields above are ignored. */
+  int32_t aniso;
+  const float *kappa_vel[3], *a_vel[3][2], *b_vel[3][2];
+  const float *kappa_prs[3], *a_prs[3][2], *b_prs[3][2];
 } fw25o_problem;
 
 /* state: p,u,v,w + 6 psi (velocity-sweep memory variables: x1,y1,z1,x2,y2,z2) + 6 phi.

@@ -36,6 +36,9 @@ class _Problem(C.Structure):
         ("ncoordsout", C.c_int32), ("outc", _I),
         ("ncoordszero", C.c_int32), ("icczero", _I),
         ("dcmap_full3d", C.c_int32), ("nX_dcmap", C.c_int32),
+        ("aniso", C.c_int32),
+        ("kappa_vel", _F * 3), ("a_vel", (_F * 2) * 3), ("b_vel", (_F * 2) * 3),
+        ("kappa_prs", _F * 3), ("a_prs", (_F * 2) * 3), ("b_prs", (_F * 2) * 3),
     ]
 
 
@@ -108,6 +111,25 @@ def _marshal(pb):
         assert a.size == n, (name, a.size, n)
         keep.append(a)
         setattr(s, name, a.ctypes.data_as(_F))
+    aniso = getattr(pb, "aniso", None)
+    if aniso:
+        # file stems of the anisotropic protocol (input_file_writer.py:592-620) -> per-axis slots
+        s.aniso = 1
+        vel, prs = aniso_axis_names(s.ndim)
+
+        def ptr(stem):
+            a = _f32(aniso[stem]).reshape(-1)
+            assert a.size == n, (stem, a.size, n)
+            keep.append(a)
+            return a.ctypes.data_as(_F)
+        for ax in range(s.ndim):
+            s.kappa_vel[ax] = ptr("kappa" + vel[ax])
+            s.kappa_prs[ax] = ptr("kappa" + prs[ax])
+            for nu in range(2):
+                s.a_vel[ax][nu] = ptr(f"apml{vel[ax]}{nu + 1}")
+                s.b_vel[ax][nu] = ptr(f"bpml{vel[ax]}{nu + 1}")
+                s.a_prs[ax][nu] = ptr(f"apml{prs[ax]}{nu + 1}")
+                s.b_prs[ax][nu] = ptr(f"bpml{prs[ax]}{nu + 1}")
     a = _f32(pb.dmap).reshape(-1)
     assert a.size == 18 * s.ndmap
     keep.append(a)
@@ -118,6 +140,8 @@ def _marshal(pb):
     s.dcmap = a.ctypes.data_as(_I)
     for cnt, name in (("ncoords", "icc"), ("ncoordsout", "outc"), ("ncoordszero", "icczero")):
         a = _i32(getattr(pb, name)).reshape(-1, s.ndim)
+        if name == "icczero" and aniso:
+            a = a[:0]            # the anisotropic binaries have no inject_source_zero kernel
         keep.append(a)
         setattr(s, cnt, a.shape[0])
         setattr(s, name, a.ctypes.data_as(_I))
@@ -125,6 +149,11 @@ def _marshal(pb):
     keep.append(a)
     s.icmat = a.ctypes.data_as(_F)
     return s, keep
+
+
+def aniso_axis_names(ndim: int):
+    """File-stem letters per axis (x, y[, z]) of the anisotropic protocol: (velocity sweep, pressure sweep)."""
+    return (("x", "y", "z")[:ndim], ("u", "w") if ndim == 2 else ("u", "v", "w"))
 
 
 def n_frames(pb) -> int:

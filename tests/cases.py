@@ -24,6 +24,14 @@ CASES_2GPU = {
 }
 CASES.update(CASES_2GPU)
 
+# The anisotropic-relaxation engine family (per-axis kappa / a / b maps, every array different): goldens from the
+# reference's fullwave2_{2d,3d}_2_relax_multi_gpu_sm_100_cuda129 binaries.
+CASES_ANISO = {
+    "aniso2d": dict(shape=(70, 76), nT=150, modT=3, seed=21, aniso=True, n_air=0),
+    "aniso3d": dict(shape=(40, 44, 46), nT=60, modT=2, seed=22, aniso=True, n_air=0),
+}
+CASES.update(CASES_ANISO)
+
 
 def make(name):
     return synthetic.make_problem(**CASES[name])

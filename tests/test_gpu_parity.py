@@ -174,3 +174,42 @@ def test_2d_ragged_grids_tiled_and_simple_sweeps(built_lib, shape, monkeypatch):
             for k in "puv":
                 np.testing.assert_array_equal(e.field(k), want[k], err_msg=f"variant {variant} rpt {rpt} field {k}")
             np.testing.assert_array_equal(e.read_frames(0, pb.n_frames), want_g, err_msg=f"variant {variant} rpt {rpt}")
+
+
+@pytest.mark.parametrize("name", sorted(cases.CASES_ANISO))
+def test_anisotropic_file_set(built_lib, name, tmp_path):
+    """Per-axis relaxation maps (the reference's second engine family): final fields == oracle; the executable
+    reads the anisotropic .dat set; with identical maps on every axis the result equals the isotropic run (and the
+    engine then runs its isotropic kernels); air voxels are ignored like the reference's anisotropic binaries do."""
+    import subprocess
+
+    from fullwave25_b200.build import CLI
+    pb = cases.make(name)
+    want_g, want = oracle.run(pb, return_fields=True)
+    with engine.Engine(pb) as e:
+        e.step(pb.nT)
+        e.sync()
+        for k in ("p", "u", "v") + (("w",) if pb.ndim == 3 else ()):
+            np.testing.assert_array_equal(e.field(k), want[k], err_msg=k)
+        np.testing.assert_array_equal(e.read_frames(0, pb.n_frames), want_g)
+    d = pb.to_dat_dir(tmp_path / "sim")
+    r = subprocess.run([str(CLI)], cwd=d, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    np.testing.assert_array_equal(np.fromfile(d / "genout.dat", np.float32).reshape(want_g.shape), want_g)
+    # identical axes -> the isotropic answer
+    kw = dict(cases.CASES[name]); kw.pop("aniso")
+    iso = synthetic_iso = __import__("fullwave25_b200.synthetic", fromlist=["x"]).make_problem(**kw)
+    same = __import__("fullwave25_b200.synthetic", fromlist=["x"]).make_problem(**kw)
+    vel = ("x", "y", "z")[: same.ndim]
+    prs = ("u", "w") if same.ndim == 2 else ("u", "v", "w")
+    same.aniso = {}
+    for letters, fam in ((vel, "x"), (prs, "u")):
+        for l in letters:
+            same.aniso["kappa" + l] = getattr(same, "kappa" + fam).copy()
+            for nu in (1, 2):
+                for ab in "ab":
+                    same.aniso[f"{ab}pml{l}{nu}"] = getattr(same, f"{ab}pml{fam}{nu}").copy()
+    same.icczero = np.array([[20, 21, 22][: same.ndim]], np.int32)      # ignored by the anisotropic family
+    got_same, st = engine.run(same.normalise())
+    np.testing.assert_array_equal(got_same, engine.run(iso)[0])
+    np.testing.assert_array_equal(got_same, oracle.run(same))

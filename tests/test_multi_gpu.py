@@ -19,20 +19,23 @@ def _n_gpus():
         return 0
 
 
+@pytest.mark.parametrize("schedule", ["serial", "concurrent"])
 @pytest.mark.parametrize("case", ["het3d", "het2d"])
-def test_two_gpus_bit_identical_to_one_domain(built_lib, case):
+def test_two_gpus_bit_identical_to_one_domain(built_lib, case, schedule):
     if _n_gpus() < 2:
         pytest.skip("needs 2 GPUs")
+    import os
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                         "--master-addr", "127.0.0.1", "--master-port", "29531", str(ROOT / "tools" / "slab_check.py"), case],
-                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+                       capture_output=True, text=True, timeout=600, cwd=ROOT,
+                       env=dict(os.environ, FW25_SLAB_SCHEDULE=schedule))
     lines = [l for l in r.stdout.splitlines() if l.startswith("SLABCHECK ")]
     assert r.returncode == 0 and lines, r.stdout[-2000:] + r.stderr[-2000:]
     verdict = json.loads(lines[-1][len("SLABCHECK "):])
     assert verdict["bit_exact"] and verdict["absmax"] > 0, verdict
 
 
-@pytest.mark.parametrize("mode", ["native", "native-copies", "torch"])
+@pytest.mark.parametrize("mode", ["native", "native-copies", "native-concurrent", "native-concurrent-copies", "torch"])
 @pytest.mark.parametrize("case", ["het3d", "het2d_long"])
 def test_in_process_device_list_bit_identical(built_lib, case, mode):
     """`engine.run(pb, device_ids=(0, 1))` -- what Launcher(cuda_device_id=[0, 1]) calls -- one host thread, two
@@ -42,7 +45,8 @@ def test_in_process_device_list_bit_identical(built_lib, case, mode):
     if _n_gpus() < 2:
         pytest.skip("needs 2 GPUs")
     import os
-    env = dict(os.environ, FW25_FUSED_HALO="0" if mode == "native-copies" else "1")
+    env = dict(os.environ, FW25_FUSED_HALO="0" if mode.endswith("copies") else "1",
+               FW25_SLAB_SCHEDULE="concurrent" if "concurrent" in mode else "serial")
     r = subprocess.run([sys.executable, str(ROOT / "tools" / "slab_check.py"), case, "2", mode.split("-")[0]],
                        capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     lines = [l for l in r.stdout.splitlines() if l.startswith("SLABCHECK ")]

@@ -89,3 +89,25 @@ def test_from_fullwave_objects_matches_protocol_fields():
     np.testing.assert_array_equal(pb.apmlu2, relax["a_pml_u2"].astype(np.float32))
     np.testing.assert_array_equal(pb.icczero, [[12, 13], [20, 5]])
     assert pb.dcmap.min() == 0 and pb.dcmap.max() == pb.ndmap - 1
+
+
+def test_anisotropic_file_set_round_trip(tmp_path):
+    """The anisotropic protocol (upstream use_isotropic_relaxation=False, input_file_writer.py:592-620): per-axis
+    kappa / a / b files next to the isotropic-named x-axis members; detected by kappay.dat."""
+    import numpy as np
+
+    from fullwave25_b200 import synthetic
+    from fullwave25_b200.problem import Problem
+    for shape in ((48, 52), (40, 42, 44)):
+        pb = synthetic.make_problem(shape, nT=10, aniso=True, n_air=0)
+        stems = Problem.aniso_stems(pb.ndim)
+        assert len(stems) == (4 + 16 if pb.ndim == 2 else 6 + 24) and set(pb.aniso) == set(stems)
+        assert np.array_equal(pb.aniso["kappax"], pb.kappax) and not np.array_equal(pb.aniso["kappay"], pb.kappax)
+        d = pb.to_dat_dir(tmp_path / f"an{pb.ndim}")
+        assert (d / "apmlw2.dat").exists() and ((d / "kappav.dat").exists() == (pb.ndim == 3))
+        back = Problem.from_dat_dir(d)
+        assert back.aniso is not None
+        for k in stems:
+            np.testing.assert_array_equal(back.aniso[k], pb.aniso[k])
+        iso = Problem.from_dat_dir(synthetic.make_problem(shape, nT=10).to_dat_dir(tmp_path / f"iso{pb.ndim}"))
+        assert iso.aniso is None

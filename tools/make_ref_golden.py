@@ -38,13 +38,21 @@ REF_BIN = {
 }
 
 
+# the anisotropic-relaxation engine family (upstream use_isotropic_relaxation=False)
+REF_BIN_ANISO = {
+    2: BINS / "2d" / "num_relax=2" / "fullwave2_2d_2_relax_multi_gpu_sm_100_cuda129",
+    3: BINS / "3d" / "num_relax=2" / "fullwave2_3d_2_relax_multi_gpu_sm_100_cuda129",
+}
+
+
 def run_reference(pb, work: Path, devices: str = "0", timeout: float = 600.0):
     """Returns (genout [n_frames, ncoordsout] float32, wall seconds, log text)."""
     if work.exists():
         shutil.rmtree(work)
     pb.to_dat_dir(work)
-    exe = work / REF_BIN[pb.ndim].name
-    shutil.copy(REF_BIN[pb.ndim], exe)
+    src = (REF_BIN_ANISO if getattr(pb, "aniso", None) else REF_BIN)[pb.ndim]
+    exe = work / src.name
+    shutil.copy(src, exe)
     exe.chmod(0o755)
     env = dict(os.environ, CUDA_VISIBLE_DEVICES=devices)
     t0 = time.time()

@@ -60,6 +60,8 @@ def main():
         want = oracle.run(pb)
         print("SLABCHECK " + json.dumps({"case": case, "world": world, "bit_exact": bool(np.array_equal(got, want)),
                                          "absmax": float(np.abs(want).max()), "n_diff": int((got != want).sum())}), flush=True)
+    torch.cuda.synchronize()
+    dist.barrier()                       # nobody tears NCCL down while a peer is still inside the gather
     eng.close()
     dist.destroy_process_group()
 
