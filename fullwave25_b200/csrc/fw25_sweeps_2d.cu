@@ -1,15 +1,17 @@
-// fw25_sweeps_2d.cu -- 2D sweeps for sm_100a: TMA-staged stencil tiles, register-held x column.
+// fw25_sweeps_2d.cu -- 2D sweeps for sm_100a: TMA-staged stencil tiles.
 //
 // The 2D grids of the shipped examples are 0.4-3 M points: the whole problem lives in L2 or
-// nearly so, a step takes tens of microseconds, and there is no third axis to march along.  So the CTA is a
-// small tile -- RPT rows (x) by 128 columns (the contiguous axis) -- whose haloed stencil field arrives with ONE
-// TMA load (cp.async.bulk.tensor.2d, out-of-range elements zero-filled); each of the 128 threads owns one
-// column, keeps the 16-point x column in registers while it walks down the RPT rows (one new LDS per row), reads
-// the 15 taps along the contiguous axis and the cross-term neighbours from shared memory, and loads the
-// point-wise arrays (coefficients, memory variables, old fields: each touched exactly once) straight from
-// global memory, one row ahead of the arithmetic.  ncu on the one-thread-per-cell kernels this replaces
-// (profiles/ncu_r01_2d.txt): 400 instructions per 32 cells, ~36 global loads of p per cell through L1/L2,
-// long-scoreboard stalls of 19 warps per issue, DRAM at 41 %.
+// nearly so, a step takes tens of microseconds, and there is no third axis to march along.  ncu on the
+// one-thread-per-cell L1/L2-path kernels (profiles/ncu_r01_2d.txt): 400 instructions per 32 cells, ~36 global loads
+// of p per cell, long-scoreboard stalls of 19 warps per issue, DRAM at 41 % -- latency-bound.  Here the CTA is a
+// small tile whose haloed stencil field arrives with ONE TMA load (cp.async.bulk.tensor.2d, out-of-range elements
+// zero-filled) while the threads already fetch their point-wise operands (coefficients, memory variables, old
+// fields: each touched exactly once, straight from global memory); all stencil taps are then LDS.
+//   * k_sweep_*_2dc<TR>  (default, TR = 2): TR rows x 128 columns, one cell per thread -- the shortest dependency
+//     chain, 32-41 registers, full occupancy; the (TR + 15)-row tile is shared by the TR rows.
+//   * k_sweep_*_2d<RPT>  (FW25_2D_TR=0): RPT rows x 128 columns, 128 threads, each thread walks down RPT rows with
+//     the 16-point x column in registers and loads the next row's operands ahead.  Fewer halo bytes per cell, but
+//     less parallelism: on a B200 every RPT > 1 lost to RPT = 1 at every 2D size (profiles/sweep_2d_r01.txt).
 //
 // Arithmetic: operation for operation the reference's (2D PTX L38-463 / L465-891; fw25_kernels.cuh);
 // bit-identical to k_sweep_*_simple<2> and the oracle.
@@ -24,6 +26,9 @@
 #include "fw25_kernels.cuh"
 #include "fw25_tma.cuh"
 
+#ifndef FW25_2D_TR_DEFAULT
+#define FW25_2D_TR_DEFAULT 2   // 2 | 4 | 8: one-cell-per-thread tiles of that height (2 measured best); 0: marching tiles (pick_rpt)
+#endif
 #ifndef FW25_WS_2D_MINB
 #define FW25_WS_2D_MINB 6   // resident CTAs per SM the register budget is sized for (80 registers, no spills)
 #endif
@@ -228,6 +233,123 @@ __global__ void __launch_bounds__(TC2, FW25_WS_2D_MINB)
   }
 }
 
+// ------------------------------------------------------------------------------------------ one cell per thread
+// TR rows x 128 columns per CTA, TR * 128 threads, one cell each: the haloed tile ((TR + 15) rows) is shared by the
+// TR rows, so a taller CTA moves fewer halo bytes per cell than TR single-row CTAs while every thread keeps the
+// shortest possible dependency chain (no marching).  The tile-height sweep on a B200 (profiles/sweep_2d_r01.txt)
+// showed the single-row marching tiles beating the taller marching ones at every 2D size -- parallelism matters
+// more than halo traffic there -- so this form keeps one cell per thread and shares the tile instead.
+template <int TR>
+__global__ void __launch_bounds__(TC2 * TR)
+    k_sweep_u_2dc(const __grid_constant__ CUtensorMap map_p, const Fields F, const Geom G,
+                  const StencilTab2 *__restrict__ tab, int a_lo, int a_hi) {
+  constexpr int HR = TR + 15, HC = TC2 + 16;
+  __shared__ alignas(128) float tile[HR][HC];   // tile[r][j] = p[a0 - 7 + r][c0 - 8 + j]
+  __shared__ uint64_t bar;
+  const int tc = threadIdx.x, tr = threadIdx.y;
+  const int c0 = blockIdx.x * TC2;
+  const int a0 = a_lo + blockIdx.y * TR;
+  if (tc == 0 && tr == 0) {
+    mbar_init(&bar, 1);
+    mbar_fence_init();
+    mbar_arrive_expect_tx(&bar, HR * HC * 4);
+    tma_load_2d(&tile[0][0], &map_p, c0 - 8, a0 - 7, &bar);
+  }
+  __syncthreads();
+  const int c = c0 + tc, a = a0 + tr;
+  const bool act = c >= M && c < G.nC - M && a < a_hi;
+  const long long i = (long long)a * G.sA + c;
+  PwU w{};
+  if (act) w = load_pw_u(F, i);
+  mbar_wait(&bar, 0);
+  if (!act) return;
+  const int sr = tr + 7, sc = tc + 8;
+  const StencilTab2 T = tab[w.ci];
+  const float D[9] = {0.f, T.d03.x, T.d03.y, T.d03.z, T.d03.w, T.d47.x, T.d47.y, T.d47.z, T.d47.w};
+  const float E = T.e.x;
+  float gA = 0.f, gC = 0.f;
+#pragma unroll
+  for (int k = 1; k <= M; ++k) {
+    gA = fma_(D[k], sub_(tile[sr + k][sc], tile[sr + 1 - k][sc]), gA);
+    gC = fma_(D[k], sub_(tile[sr][sc + k], tile[sr][sc + 1 - k]), gC);
+  }
+  const float pcen = tile[sr][sc], p11 = tile[sr + 1][sc + 1];
+  float cA = sub_(p11, tile[sr][sc + 1]);
+  cA = add_(cA, tile[sr + 1][sc - 1]); cA = sub_(cA, tile[sr][sc - 1]);
+  float cC = sub_(p11, tile[sr + 1][sc]);
+  cC = add_(cC, tile[sr - 1][sc + 1]); cC = sub_(cC, tile[sr - 1][sc]);
+  const float dX = G.dX;
+  gA = div_(fma_(E, cA, gA), dX);
+  gC = div_(fma_(E, cC, gC), dX);
+  const float s = div_(div_(G.dT, w.rho), fma_(rcp_(w.K), pcen, 1.0f));
+  const float mA1 = fma_(w.b1, w.mA1, mul_(gA, w.a1));
+  const float mA2 = fma_(w.b2, w.mA2, mul_(gA, w.a2));
+  const float mC1 = fma_(w.b1, w.mC1, mul_(gC, w.a1));
+  const float mC2 = fma_(w.b2, w.mC2, mul_(gC, w.a2));
+  const float qA = fma_(-s, add_(add_(div_(gA, w.kx), mA1), mA2), w.qA);
+  const float qC = fma_(-s, add_(add_(div_(gC, w.kx), mC1), mC2), w.qC);
+  __stcs(F.psi[0][0] + i, mA1); __stcs(F.psi[0][1] + i, mA2);
+  __stcs(F.psi[2][0] + i, mC1); __stcs(F.psi[2][1] + i, mC2);
+  F.q[0][i] = qA; F.q[2][i] = qC;
+}
+
+template <int TR>
+__global__ void __launch_bounds__(TC2 * TR)
+    k_sweep_p_2dc(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_v, const Fields F,
+                  const Geom G, const StencilTab2 *__restrict__ tab, int a_lo, int a_hi) {
+  constexpr int UR = TR + 15, UC = TC2 + 8;      // tu[r][j] = u[a0 - 8 + r][c0 - 4 + j]
+  constexpr int VR = TR + 2, VC = TC2 + 16;      // tv[r][j] = v[a0 - 1 + r][c0 - 8 + j]
+  __shared__ alignas(128) float tu[UR][UC];
+  __shared__ alignas(128) float tv[VR][VC];
+  __shared__ uint64_t bar;
+  const int tc = threadIdx.x, tr = threadIdx.y;
+  const int c0 = blockIdx.x * TC2;
+  const int a0 = a_lo + blockIdx.y * TR;
+  if (tc == 0 && tr == 0) {
+    mbar_init(&bar, 1);
+    mbar_fence_init();
+    mbar_arrive_expect_tx(&bar, (UR * UC + VR * VC) * 4);
+    tma_load_2d(&tu[0][0], &map_u, c0 - 4, a0 - 8, &bar);
+    tma_load_2d(&tv[0][0], &map_v, c0 - 8, a0 - 1, &bar);
+  }
+  __syncthreads();
+  const int c = c0 + tc, a = a0 + tr;
+  const bool act = c >= M && c < G.nC - M && a < a_hi;
+  const long long i = (long long)a * G.sA + c;
+  PwP w{};
+  if (act) w = load_pw_p(F, i);
+  mbar_wait(&bar, 0);
+  if (!act) return;
+  const int su = tc + 4, sv = tc + 8, ur = tr + 8, vr = tr + 1;
+  const StencilTab2 T = tab[w.ci];
+  const float D[9] = {0.f, T.d03.x, T.d03.y, T.d03.z, T.d03.w, T.d47.x, T.d47.y, T.d47.z, T.d47.w};
+  const float E = T.e.x;
+  float hA = 0.f, hC = 0.f;
+#pragma unroll
+  for (int k = 1; k <= M; ++k) {
+    hA = fma_(D[k], sub_(tu[ur + k - 1][su], tu[ur - k][su]), hA);
+    hC = fma_(D[k], sub_(tv[vr][sv + k - 1], tv[vr][sv - k]), hC);
+  }
+  float cA = sub_(tu[ur][su + 1], tu[ur - 1][su + 1]);
+  cA = add_(cA, tu[ur][su - 1]); cA = sub_(cA, tu[ur - 1][su - 1]);
+  float cC = sub_(tv[vr + 1][sv], tv[vr + 1][sv - 1]);
+  cC = add_(cC, tv[vr - 1][sv]); cC = sub_(cC, tv[vr - 1][sv - 1]);
+  const float dX = G.dX;
+  hA = div_(fma_(E, cA, hA), dX);
+  hC = div_(fma_(E, cC, hC), dX);
+  const float fA1 = fma_(w.b1, w.fA1, mul_(hA, w.a1));
+  const float fA2 = fma_(w.b2, w.fA2, mul_(hA, w.a2));
+  const float fC1 = fma_(w.b1, w.fC1, mul_(hC, w.a1));
+  const float fC2 = fma_(w.b2, w.fC2, mul_(hC, w.a2));
+  float S = add_(div_(hA, w.ku), div_(hC, w.ku));
+  S = add_(fA1, S); S = add_(fA2, S); S = add_(fC1, S); S = add_(fC2, S);
+  const float At = mul_(mul_(G.dT, w.K), S);
+  const float Bt = fma_(w.p, mul_(rcp_(w.K), sub_(1.0f, add_(w.beta, w.beta))), 1.0f);
+  __stcs(F.phi[0][0] + i, fA1); __stcs(F.phi[0][1] + i, fA2);
+  __stcs(F.phi[2][0] + i, fC1); __stcs(F.phi[2][1] + i, fC2);
+  F.p[i] = fma_(-At, Bt, w.p);
+}
+
 // ------------------------------------------------------------------------------------------ host
 using EncodeFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                               const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -279,12 +401,11 @@ bool sweeps2d_supported(int ndim, const Geom &G) {
   return ndim == 2 && G.nB == 1 && G.pitch % 32 == 0 && G.nC > 2 * M && encode_fn_2d() != nullptr;
 }
 
-// Below ~0.8 M cells per launch the one-thread-per-cell kernels win: such a grid is L2-resident and has too few
-// cells to keep 148 SMs busy with 4 cells per thread (B200, profiles/sweep_2d_r01.txt: 0.52 M cells 21.6 vs 17.7
-// Gpt/s, 1.05 M cells 24.0 vs 27.0, 3.2 M cells 23.6 vs 30.2).  FW25_2D_MIN_CELLS overrides the threshold.
+// The tiled sweeps beat the L1/L2-path kernels at every 2D size measured (0.39 M .. 3.2 M cells: +26 .. +40 %,
+// profiles/sweep_2d_r01.txt), so auto mode always takes them; FW25_2D_MIN_CELLS sets a floor for experiments.
 bool sweeps2d_worthwhile(const Geom &G, int rows) {
   const char *ev = getenv("FW25_2D_MIN_CELLS");
-  const long long thr = ev ? atoll(ev) : 786432;
+  const long long thr = ev ? atoll(ev) : 0;
   return (long long)rows * G.nC >= thr;
 }
 
@@ -322,18 +443,34 @@ void plan2d_destroy(Plan2D *pl) {
   delete pl;
 }
 
-// rows per CTA: 8 when that still gives every SM several waves of CTAs, else 4 (small grids need the parallelism
-// more than they need the shorter halo); FW25_2D_RPT overrides
+// rows per thread of the marching tiles.  Measured on a B200 at every 2D size from 0.39 M to 3.2 M cells
+// (profiles/sweep_2d_r01.txt): 1 row beats 2 beats 4 beats 8 -- the 16-row haloed tile comes out of L2 through TMA
+// for next to nothing, parallelism and short dependency chains are what pays.  FW25_2D_RPT overrides.
 static int pick_rpt(const Geom &G, int rows) {
+  (void)G; (void)rows;
   const char *ev = getenv("FW25_2D_RPT");
   const int env = ev ? atoi(ev) : 0;
   if (env == 1 || env == 2 || env == 4 || env == 8) return env;
-  const long long ctas8 = (long long)((G.nC - M + TC2 - 1) / TC2) * ((rows + 7) / 8);
-  return ctas8 >= 148LL * FW25_WS_2D_MINB * 2 ? 8 : 4;
+  return 1;
+}
+
+// FW25_2D_TR = 2 | 4 | 8: one-cell-per-thread tiles of that many rows (default, see pick_tr); 0: marching tiles
+static int pick_tr() {
+  const char *ev = getenv("FW25_2D_TR");
+  const int v = ev ? atoi(ev) : FW25_2D_TR_DEFAULT;
+  return (v == 2 || v == 4 || v == 8) ? v : 0;
 }
 
 int launch_sweep_u_2d(const Plan2D *pl, const Fields &F, const Geom &G, int a_lo, int a_hi, cudaStream_t st) {
   if (a_hi <= a_lo) return 0;
+  if (const int tr = pick_tr()) {
+    dim3 grd((G.nC - M + TC2 - 1) / TC2, (a_hi - a_lo + tr - 1) / tr, 1), blk(TC2, tr, 1);
+    const CUtensorMap &mp = pl->p[rpt_slot(tr)];
+    if (tr == 8) k_sweep_u_2dc<8><<<grd, blk, 0, st>>>(mp, F, G, pl->tab, a_lo, a_hi);
+    else if (tr == 4) k_sweep_u_2dc<4><<<grd, blk, 0, st>>>(mp, F, G, pl->tab, a_lo, a_hi);
+    else k_sweep_u_2dc<2><<<grd, blk, 0, st>>>(mp, F, G, pl->tab, a_lo, a_hi);
+    return 1;
+  }
   const int rpt = pick_rpt(G, a_hi - a_lo);
   dim3 grd((G.nC - M + TC2 - 1) / TC2, (a_hi - a_lo + rpt - 1) / rpt, 1);
   const CUtensorMap &mp = pl->p[rpt_slot(rpt)];
@@ -346,6 +483,14 @@ int launch_sweep_u_2d(const Plan2D *pl, const Fields &F, const Geom &G, int a_lo
 
 int launch_sweep_p_2d(const Plan2D *pl, const Fields &F, const Geom &G, int a_lo, int a_hi, cudaStream_t st) {
   if (a_hi <= a_lo) return 0;
+  if (const int tr = pick_tr()) {
+    dim3 grd((G.nC - M + TC2 - 1) / TC2, (a_hi - a_lo + tr - 1) / tr, 1), blk(TC2, tr, 1);
+    const CUtensorMap &mu = pl->u[rpt_slot(tr)], &mv = pl->v[rpt_slot(tr)];
+    if (tr == 8) k_sweep_p_2dc<8><<<grd, blk, 0, st>>>(mu, mv, F, G, pl->tab, a_lo, a_hi);
+    else if (tr == 4) k_sweep_p_2dc<4><<<grd, blk, 0, st>>>(mu, mv, F, G, pl->tab, a_lo, a_hi);
+    else k_sweep_p_2dc<2><<<grd, blk, 0, st>>>(mu, mv, F, G, pl->tab, a_lo, a_hi);
+    return 1;
+  }
   const int rpt = pick_rpt(G, a_hi - a_lo);
   dim3 grd((G.nC - M + TC2 - 1) / TC2, (a_hi - a_lo + rpt - 1) / rpt, 1);
   const CUtensorMap &mu = pl->u[rpt_slot(rpt)], &mv = pl->v[rpt_slot(rpt)];

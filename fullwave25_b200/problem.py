@@ -241,6 +241,10 @@ class Problem:
         d_tab, dmap, dcmap, ndmap = stencil.tables(c, dt=grid.dt, dx=grid.dx, cfl=grid.cfl, is_3d=is_3d)
         relax = medium.relaxation_param_dict_for_fw2
         maps = {dat: relax[py] for py, dat in _RELAX_RENAME.items()}
+        aniso = None
+        if "kappa_y" in relax:       # use_isotropic_relaxation=False upstream: per-axis maps (a_pml_y1 -> apmly1.dat)
+            aniso = {key.replace("_", ""): relax[key] for key in relax
+                     if key.replace("_", "") in cls.aniso_stems(3 if is_3d else 2)}
         icmat = np.asarray(source.icmat)
         air = np.asarray(medium.air_map)
         pb = cls(
@@ -253,6 +257,7 @@ class Problem:
             outc=np.asarray(sensor.outcoords),
             icczero=np.stack(np.nonzero(air != 0), axis=1) if air.any() else np.zeros((0, c.ndim), np.int32),
             extra={"c": c, "d": d_tab, "dY": grid.dy, "dZ": getattr(grid, "dz", grid.dx), "c0": grid.c0},
+            aniso=aniso,
         )
         return pb.normalise()
 

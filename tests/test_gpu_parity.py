@@ -166,14 +166,18 @@ def test_2d_ragged_grids_tiled_and_simple_sweeps(built_lib, shape, monkeypatch):
     from fullwave25_b200 import synthetic
     pb = synthetic.make_problem(shape, nT=90, modT=4, seed=31, n_pml=9, n_trans=5, block=7, n_sensors=120, n_air=20)
     want_g, want = oracle.run(pb, return_fields=True)
-    for variant, rpt in ((1, "0"), (2, "4"), (2, "8"), (0, "0")):
+    # (variant, rows per thread of the marching tiles, rows per CTA of the one-cell-per-thread tiles)
+    for variant, rpt, tr in ((1, "0", "0"), (2, "1", "0"), (2, "2", "0"), (2, "4", "0"), (2, "8", "0"),
+                             (2, "0", "2"), (2, "0", "4"), (2, "0", "8"), (0, "0", "0")):
         monkeypatch.setenv("FW25_2D_RPT", rpt)
+        monkeypatch.setenv("FW25_2D_TR", tr)
         with engine.Engine(pb, variant=variant) as e:
             e.step(pb.nT)
             e.sync()
+            tag = f"variant {variant} rpt {rpt} tr {tr}"
             for k in "puv":
-                np.testing.assert_array_equal(e.field(k), want[k], err_msg=f"variant {variant} rpt {rpt} field {k}")
-            np.testing.assert_array_equal(e.read_frames(0, pb.n_frames), want_g, err_msg=f"variant {variant} rpt {rpt}")
+                np.testing.assert_array_equal(e.field(k), want[k], err_msg=f"{tag} field {k}")
+            np.testing.assert_array_equal(e.read_frames(0, pb.n_frames), want_g, err_msg=tag)
 
 
 @pytest.mark.parametrize("name", sorted(cases.CASES_ANISO))

@@ -77,10 +77,10 @@ def build(user_shape, *, f0=1e6, c0=1540.0, ppw=12, cfl=0.2, n_steps=None, block
     return fw, grid, medium, source, sensor
 
 
-def ref_bin(ndim: int) -> Path:
+def ref_bin(ndim: int, isotropic: bool = True) -> Path:
     for base in (ROOT / "baseline" / "_ref", Path("/root/reference")):
         p = (base / "fullwave" / "solver" / "bins" / "gpu" / f"{ndim}d" / "num_relax=2" /
-             f"fullwave2_{ndim}d_2_relax_isotropic_multi_gpu_sm_100_cuda129")
+             f"fullwave2_{ndim}d_2_relax_{'isotropic_' if isotropic else ''}multi_gpu_sm_100_cuda129")
         if p.exists():
             return p
     raise FileNotFoundError("reference sm_100 executable not found (run tools/install_reference.sh)")
