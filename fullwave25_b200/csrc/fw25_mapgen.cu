@@ -1,0 +1,389 @@
+// fw25_mapgen.cu -- the engine's 13 coefficient maps + dcmap built on the GPU (include/fw25.h, fw25_mapgen).
+//
+// What it replaces, upstream (all float64 numpy on one host thread, over the EXTENDED grid):
+//   pml_builder.py:321-704   _extend_map_for_pml        pad the user-grid maps by edge replication
+//   pml_builder.py:842-1254  _apply_pml / _apply_pml_3d  per key: ramp d / alpha towards the PML target, axis by axis
+//   pml_builder.py:1256-1498 _apply_transition_and_pml   one axis: rim + layers := target, 1-D ramp next to it
+//   pml_builder.py:794-810   _calc_a_and_b               b = exp(-(d/kappa + alpha) dt), a = d/(kappa (d + kappa alpha) + 1e-10) (b - 1)
+//   medium.py:256-259        bulk_modulus                K = c^2 rho
+//   input_file_writer.py:95-103, :558-559, :870-881      dcmap = round(c + 1e-9) - round(min c + 1e-9); float32 casts
+//   utils/relaxation_parameters.py:18-75                 (optional) nearest-bin look-up of the 10 relaxation parameters
+//
+// One thread per extended voxel.  The axis-by-axis in-place passes of the reference collapse to a closed form per
+// voxel: every ramp takes its "face" value from the first user-grid cell along that axis, and the pad is an edge
+// replication, so the value entering the ramps is the user-grid value at the CLAMPED coordinate, and the passes are
+//   v <- target                         where the axis index lies in the rim / fully damped layers,
+//   v <- v - tf * (v - target)          inside the 1-D ramp,
+//   v unchanged                         elsewhere,
+// applied for axis 0, 1[, 2] in that order.  Each step is the same float64 operation numpy performs (explicit _rn
+// intrinsics, nothing contracted), so d / alpha after the ramps are bit-identical to the reference's and the float32
+// maps differ only where exp() differs in its last float64 bit (<= 1 float32 ulp in a, b).
+// HBM traffic per extended voxel: <= 13 float64 reads of the (13x smaller, mostly L2-resident) user grid + 14 x 4 B
+// written: the kernel is bound by the 56 B/voxel it writes.
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/fw25.h"
+
+namespace fw25 {
+extern thread_local std::string g_err;
+
+namespace {
+
+struct MgFail {
+  int code;
+};
+
+#define MG_CUDA(expr)                                                                               \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess) {                                                                        \
+      char _b[512];                                                                                 \
+      snprintf(_b, sizeof _b, "CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, __LINE__, \
+               cudaGetErrorString(_e));                                                             \
+      g_err = _b;                                                                                   \
+      throw MgFail{2};                                                                              \
+    }                                                                                               \
+  } while (0)
+
+void mg_fail(const std::string &msg) {
+  g_err = msg;
+  throw MgFail{1};
+}
+
+// ramp codes in the per-axis weight tables
+constexpr double W_KEEP = 2.0;     // outside every layer: value unchanged
+constexpr double W_TARGET = -1.0;  // rim / fully damped layers: value := target
+// anything else: the transition-function sample tf in [0, 1]
+
+struct MgParams {
+  int ndim;
+  int nA, nB, nC, pitch;   // extended grid in the engine's layout: 3D (x, y, z); 2D (x, -, y) with nB = 1
+  int uA, uB, uC;          // user grid, same axis mapping
+  int nb;                  // boundary points per side: M + n_pml + n_transition
+  int use_pml;
+  double dt, d_target;
+  // weight tables [3 ramp kinds][axis length], one per engine axis (B unused in 2D): kind 0 polynomial (d nu1),
+  // 1 linear (alpha nu1), 2 cosine (d, alpha nu2)
+  const double *wA, *wB, *wC;
+  const double *c, *rho, *beta;
+  const double *relax[10];
+  const double *alpha_coeff, *alpha_power, *lut, *lut_alpha, *lut_power;
+  const unsigned char *lut_invalid;
+  int lut_na, lut_np;
+  double alpha_min, alpha_max, power_min, power_max;
+  int c_round_min;
+  long long dcmap_limit;   // flat dense indices >= limit read 0 (reference 3D binary); < 0: no limit
+  float *out[13];          // rho K beta kappax kappau apmlx1 bpmlx1 apmlx2 bpmlx2 apmlu1 bpmlu1 apmlu2 bpmlu2
+  int32_t *dcmap;
+  unsigned long long *invalid_count;
+};
+
+__device__ __forceinline__ double ramp(double v, double w, double target) {
+  if (w == W_KEEP) return v;
+  if (w == W_TARGET) return target;
+  return __dsub_rn(v, __dmul_rn(w, __dsub_rn(v, target)));   // up_vals - tf * (up_vals - value_target)
+}
+
+// np.searchsorted(list, v) (side = "left") clipped to [0, n - 1]: first i with list[i] >= v
+__device__ __forceinline__ int search_left(const double *__restrict__ list, int n, double v) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(list + mid) < v) lo = mid + 1; else hi = mid;
+  }
+  return min(lo, n - 1);
+}
+
+__device__ __forceinline__ double clip(double v, double lo, double hi) { return fmin(fmax(v, lo), hi); }   // np.clip
+
+__device__ __forceinline__ void a_and_b(double d, double kappa, double alpha, double dt, float &a, float &b) {
+  // b = np.exp(-(d_x / kappa_x + alpha_x) * dt)
+  const double bb = exp(__dmul_rn(-__dadd_rn(__ddiv_rn(d, kappa), alpha), dt));
+  // a = d_x / (kappa_x * (d_x + kappa_x * alpha_x) + eps) * (b - 1)
+  const double den = __dadd_rn(__dmul_rn(kappa, __dadd_rn(d, __dmul_rn(kappa, alpha))), 1e-10);
+  const double aa = __dmul_rn(__ddiv_rn(d, den), __dsub_rn(bb, 1.0));
+  a = __double2float_rn(aa);
+  b = __double2float_rn(bb);
+}
+
+__global__ void __launch_bounds__(256) k_mapgen(const MgParams P) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;   // contiguous axis (incl. the padding columns)
+  const int b = blockIdx.y;
+  const int a = blockIdx.z;
+  if (c >= P.pitch) return;
+  const long long o = ((long long)a * P.nB + b) * P.pitch + c;
+  if (c >= P.nC) {   // padding: zeros, like the engine's own uploads
+#pragma unroll
+    for (int i = 0; i < 13; ++i) P.out[i][o] = 0.0f;
+    P.dcmap[o] = 0;
+    return;
+  }
+  const int ua = min(max(a - P.nb, 0), P.uA - 1);
+  const int ub = min(max(b - P.nb, 0), P.uB - 1);
+  const int uc = min(max(c - P.nb, 0), P.uC - 1);
+  const long long u = ((long long)ua * P.uB + ub) * P.uC + uc;
+
+  const double cs = __ldg(P.c + u), rho = __ldg(P.rho + u);
+  P.out[0][o] = __double2float_rn(rho);
+  P.out[1][o] = __double2float_rn(__dmul_rn(__dmul_rn(cs, cs), rho));   // np.multiply(sound_speed**2, density)
+  P.out[2][o] = __double2float_rn(__ldg(P.beta + u));
+  {
+    const long long dense = ((long long)a * P.nB + b) * P.nC + c;
+    int dc = (int)rint(__dadd_rn(cs, 1e-9)) - P.c_round_min;   // np.round(c + 1e-9): ties to even, like rint
+    if (P.dcmap_limit >= 0 && dense >= P.dcmap_limit) dc = 0;
+    P.dcmap[o] = dc;
+  }
+
+  double r[10];
+  if (P.relax[0]) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) r[i] = __ldg(P.relax[i] + u);
+  } else {
+    const double al = clip(__ldg(P.alpha_coeff + u), P.alpha_min, P.alpha_max);
+    const double pw = clip(__ldg(P.alpha_power + u), P.power_min, P.power_max);
+    const int ia = search_left(P.lut_alpha, P.lut_na, al);
+    const int ip = search_left(P.lut_power, P.lut_np, pw);
+    const long long e = (long long)ia * P.lut_np + ip;
+    if (P.lut_invalid && P.lut_invalid[e]) atomicAdd(P.invalid_count, 1ULL);
+#pragma unroll
+    for (int i = 0; i < 10; ++i) r[i] = __ldg(P.lut + e * 10 + i);
+  }
+
+  if (P.use_pml) {
+    // axis order 0, 1[, 2] == engine axes A, (B,) C; 2D has no B
+    const double *w[3] = {P.wA, P.ndim == 3 ? P.wB : nullptr, P.wC};
+    const int n[3] = {P.nA, P.nB, P.nC};
+    const int at[3] = {a, b, c};
+#pragma unroll
+    for (int ax = 0; ax < 3; ++ax) {
+      if (!w[ax]) continue;
+      const double wp = __ldg(w[ax] + at[ax]), wl = __ldg(w[ax] + n[ax] + at[ax]), wc = __ldg(w[ax] + 2 * n[ax] + at[ax]);
+      r[2] = ramp(r[2], wp, P.d_target);  r[4] = ramp(r[4], wp, P.d_target);   // d_x1_nu1, d_x2_nu1: polynomial -> d_target_pml
+      r[3] = ramp(r[3], wl, 0.0);         r[5] = ramp(r[5], wl, 0.0);          // alpha_*_nu1: linear -> 0
+      r[6] = ramp(r[6], wc, 0.0);         r[8] = ramp(r[8], wc, 0.0);          // d_*_nu2: cosine -> 0
+      r[7] = ramp(r[7], wc, 0.0);         r[9] = ramp(r[9], wc, 0.0);          // alpha_*_nu2: cosine -> 0
+    }
+  }
+  // kappa_x <- kappa_x2, kappa_u <- kappa_x1; "x" family (velocity sweep) <- x2, "u" family (pressure sweep) <- x1
+  P.out[3][o] = __double2float_rn(r[1]);
+  P.out[4][o] = __double2float_rn(r[0]);
+  float fa, fb;
+  a_and_b(r[4], r[1], r[5], P.dt, fa, fb);  P.out[5][o] = fa;  P.out[6][o] = fb;    // apmlx1, bpmlx1
+  a_and_b(r[8], r[1], r[9], P.dt, fa, fb);  P.out[7][o] = fa;  P.out[8][o] = fb;    // apmlx2, bpmlx2
+  a_and_b(r[2], r[0], r[3], P.dt, fa, fb);  P.out[9][o] = fa;  P.out[10][o] = fb;   // apmlu1, bpmlu1
+  a_and_b(r[6], r[0], r[7], P.dt, fa, fb);  P.out[11][o] = fa; P.out[12][o] = fb;   // apmlu2, bpmlu2
+}
+
+// Per-axis weight table of one ramp kind (pml_builder.py:1282-1294, :1340-1375): n = extended axis length,
+// thickness / offset in cells, tf = the transition function sampled on thickness + 1 points.
+void fill_weights(double *w, int n, int m, int thickness, int offset, const double *tf) {
+  for (int i = 0; i < n; ++i) w[i] = W_KEEP;
+  const int lo_set = m + offset + thickness;                  // input_array[: M + offset + thickness] = target
+  const int hi_set = n - m - thickness - offset;              // input_array[n - M - thickness - offset :] = target
+  for (int i = 0; i < n; ++i)
+    if (i < lo_set || i >= hi_set) w[i] = W_TARGET;
+  const int up_start = m + offset - 1, up_end = m + offset + thickness;
+  for (int i = up_start; i < up_end; ++i)                     // reversed transition function
+    if (i >= 0 && i < n) w[i] = tf[thickness - (i - up_start)];
+  const int down_start = n - m - thickness - offset - 1, down_end = n - m - offset;
+  for (int i = down_start; i < down_end; ++i)                 // forward transition function (written second: it wins)
+    if (i >= 0 && i < n) w[i] = tf[i - down_start];
+}
+
+}  // namespace
+}  // namespace fw25
+
+using namespace fw25;
+
+struct fw25_mapset {
+  int device = 0;
+  int ndim = 3, nX = 0, nY = 0, nZ = 1, pitch = 0;
+  int dcmap_full3d = 1;
+  size_t cells = 0;
+  float *maps[13] = {};
+  int32_t *dcmap = nullptr;
+  long long invalid = 0;
+  ~fw25_mapset() {
+    cudaSetDevice(device);
+    for (float *m : maps)
+      if (m) cudaFree(m);
+    if (dcmap) cudaFree(dcmap);
+  }
+};
+
+static const char *const kMapNames[13] = {"rho",    "K",      "beta",   "kappax", "kappau", "apmlx1", "bpmlx1",
+                                          "apmlx2", "bpmlx2", "apmlu1", "bpmlu1", "apmlu2", "bpmlu2"};
+
+extern "C" {
+
+int fw25_mapgen(const fw25_medium *md, int32_t device, fw25_mapset **out, double *stats_ms) {
+  if (!md || !out) { g_err = "fw25_mapgen: NULL argument"; return 1; }
+  *out = nullptr;
+  std::unique_ptr<fw25_mapset> ms(new fw25_mapset());
+  std::vector<void *> tmp;   // device scratch: user-grid inputs, tables
+  cudaEvent_t ev[3] = {};
+  int rc = 0;
+  try {
+    if (md->ndim != 2 && md->ndim != 3) mg_fail("fw25_mapgen: ndim must be 2 or 3");
+    const int ndim = md->ndim;
+    const int nz_u = ndim == 3 ? md->nz : 1;
+    if (md->nx <= 0 || md->ny <= 0 || nz_u <= 0) mg_fail("fw25_mapgen: user grid dimensions must be positive");
+    const int m = md->m_spatial_order, npml = md->n_pml_layer, ntr = md->n_transition_layer;
+    if (m < 0 || npml < 0 || ntr < 0) mg_fail("fw25_mapgen: negative layer count");
+    if (md->use_pml && ntr == 0)   // pml_builder.py:1275-1281 (the nu = 2 keys transit within the transition layer)
+      mg_fail("Transition layer is not defined. Set transit_within_transition_layer to False or define n_transition_layer.");
+    if (!md->sound_speed || !md->density || !md->beta) mg_fail("fw25_mapgen: sound_speed / density / beta is NULL");
+    const bool direct = md->relax[0] != nullptr;
+    if (direct) {
+      for (int i = 0; i < 10; ++i)
+        if (!md->relax[i]) mg_fail("fw25_mapgen: a relaxation-parameter map is NULL");
+    } else {
+      if (!md->alpha_coeff || !md->alpha_power || !md->lut || !md->lut_alpha || !md->lut_power || md->lut_na <= 0 ||
+          md->lut_np <= 0)
+        mg_fail("fw25_mapgen: neither relaxation maps nor a complete look-up table were given");
+    }
+    if (md->use_pml && (!md->tf_polynomial || !md->tf_linear || !md->tf_cosine))
+      mg_fail("fw25_mapgen: a transition-function table is NULL");
+    const int nb = m + npml + ntr;
+    const long long ex = md->nx + 2LL * nb, ey = md->ny + 2LL * nb, ez = ndim == 3 ? nz_u + 2LL * nb : 1;
+    if (ex > INT32_MAX || ey > INT32_MAX || ez > INT32_MAX) mg_fail("fw25_mapgen: extended grid too large");
+
+    MG_CUDA(cudaSetDevice(device));
+    ms->device = device;
+    ms->ndim = ndim; ms->nX = (int)ex; ms->nY = (int)ey; ms->nZ = (int)ez;
+    ms->dcmap_full3d = md->dcmap_full3d != 0 || ndim == 2;
+
+    MgParams P{};
+    P.ndim = ndim;
+    P.nA = (int)ex; P.nB = ndim == 3 ? (int)ey : 1; P.nC = ndim == 3 ? (int)ez : (int)ey;
+    P.uA = md->nx; P.uB = ndim == 3 ? md->ny : 1; P.uC = ndim == 3 ? nz_u : md->ny;
+    P.pitch = fw25_pitch(P.nC);
+    ms->pitch = P.pitch;
+    P.nb = nb; P.use_pml = md->use_pml != 0;
+    P.dt = md->dt; P.d_target = md->d_target_pml;
+    P.c_round_min = md->c_round_min;
+    P.dcmap_limit = (ndim == 3 && !md->dcmap_full3d) ? ex * ey : -1;
+    P.lut_na = md->lut_na; P.lut_np = md->lut_np;
+    P.alpha_min = md->alpha_min; P.alpha_max = md->alpha_max; P.power_min = md->power_min; P.power_max = md->power_max;
+
+    cudaStream_t st = nullptr;   // setup path: the legacy default stream orders uploads, kernel and frees
+    for (auto &e : ev) MG_CUDA(cudaEventCreate(&e));
+    MG_CUDA(cudaEventRecord(ev[0], st));
+    const size_t upts = (size_t)md->nx * md->ny * nz_u;
+    auto up = [&](const void *host, size_t bytes) -> void * {
+      void *d = nullptr;
+      MG_CUDA(cudaMalloc(&d, bytes ? bytes : 8));
+      tmp.push_back(d);
+      if (bytes) MG_CUDA(cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, st));
+      return d;
+    };
+    P.c = (const double *)up(md->sound_speed, upts * 8);
+    P.rho = (const double *)up(md->density, upts * 8);
+    P.beta = (const double *)up(md->beta, upts * 8);
+    if (direct) {
+      for (int i = 0; i < 10; ++i) P.relax[i] = (const double *)up(md->relax[i], upts * 8);
+    } else {
+      P.alpha_coeff = (const double *)up(md->alpha_coeff, upts * 8);
+      P.alpha_power = (const double *)up(md->alpha_power, upts * 8);
+      P.lut = (const double *)up(md->lut, (size_t)md->lut_na * md->lut_np * 10 * 8);
+      P.lut_alpha = (const double *)up(md->lut_alpha, (size_t)md->lut_na * 8);
+      P.lut_power = (const double *)up(md->lut_power, (size_t)md->lut_np * 8);
+      if (md->lut_invalid) P.lut_invalid = (const unsigned char *)up(md->lut_invalid, (size_t)md->lut_na * md->lut_np);
+    }
+    if (P.use_pml) {
+      const int len[3] = {P.nA, P.nB, P.nC};
+      const double **slot[3] = {&P.wA, &P.wB, &P.wC};
+      for (int ax = 0; ax < 3; ++ax) {
+        if (ndim == 2 && ax == 1) continue;
+        std::vector<double> w((size_t)3 * len[ax]);
+        fill_weights(w.data(), len[ax], m, npml + ntr, 0, md->tf_polynomial);
+        fill_weights(w.data() + len[ax], len[ax], m, npml + ntr, 0, md->tf_linear);
+        fill_weights(w.data() + 2 * (size_t)len[ax], len[ax], m, ntr, npml, md->tf_cosine);
+        *slot[ax] = (const double *)up(w.data(), w.size() * 8);
+        MG_CUDA(cudaStreamSynchronize(st));   // w goes out of scope
+      }
+    }
+    unsigned long long *d_inv = (unsigned long long *)up(nullptr, 0);
+    MG_CUDA(cudaMemsetAsync(d_inv, 0, 8, st));
+    P.invalid_count = d_inv;
+
+    ms->cells = (size_t)P.nA * P.nB * P.pitch;
+    for (int i = 0; i < 13; ++i) {
+      MG_CUDA(cudaMalloc((void **)&ms->maps[i], ms->cells * 4));
+      P.out[i] = ms->maps[i];
+    }
+    MG_CUDA(cudaMalloc((void **)&ms->dcmap, ms->cells * 4));
+    P.dcmap = ms->dcmap;
+
+    if (P.nB > 65535 || P.nA > 65535) mg_fail("fw25_mapgen: more than 65535 rows per axis");
+    MG_CUDA(cudaEventRecord(ev[1], st));
+    dim3 grid((P.pitch + 255) / 256, P.nB, P.nA);
+    k_mapgen<<<grid, 256, 0, st>>>(P);
+    MG_CUDA(cudaGetLastError());
+    MG_CUDA(cudaEventRecord(ev[2], st));
+    unsigned long long inv = 0;
+    MG_CUDA(cudaMemcpyAsync(&inv, d_inv, 8, cudaMemcpyDeviceToHost, st));
+    MG_CUDA(cudaStreamSynchronize(st));
+    ms->invalid = (long long)inv;
+    if (stats_ms) {
+      float a = 0, b = 0;
+      MG_CUDA(cudaEventElapsedTime(&a, ev[0], ev[1]));
+      MG_CUDA(cudaEventElapsedTime(&b, ev[1], ev[2]));
+      stats_ms[0] = a; stats_ms[1] = b;
+    }
+  } catch (const MgFail &f) {
+    rc = f.code;
+  }
+  for (void *d : tmp) cudaFree(d);
+  for (auto &e : ev)
+    if (e) cudaEventDestroy(e);
+  if (rc) return rc;
+  *out = ms.release();
+  return 0;
+}
+
+int fw25_mapset_problem(const fw25_mapset *ms, fw25_problem *pb) {
+  if (!ms || !pb) { g_err = "fw25_mapset_problem: NULL argument"; return 1; }
+  pb->ndim = ms->ndim; pb->nX = ms->nX; pb->nY = ms->nY; pb->nZ = ms->nZ;
+  const float **slot[13] = {&pb->rho,    &pb->K,      &pb->beta,   &pb->kappax, &pb->kappau, &pb->apmlx1, &pb->bpmlx1,
+                            &pb->apmlx2, &pb->bpmlx2, &pb->apmlu1, &pb->bpmlu1, &pb->apmlu2, &pb->bpmlu2};
+  for (int i = 0; i < 13; ++i) *slot[i] = ms->maps[i];
+  pb->dcmap = ms->dcmap;
+  pb->maps_on_device = 1;
+  pb->map_pitch = ms->pitch;
+  pb->dcmap_full3d = 1;   // the reference binary's truncation, when asked for, is already in the generated dcmap
+  pb->aniso = nullptr;
+  return 0;
+}
+
+int fw25_mapset_read(const fw25_mapset *ms, const char *name, void *out) {
+  if (!ms || !name || !out) { g_err = "fw25_mapset_read: NULL argument"; return 1; }
+  const void *src = nullptr;
+  if (!strcmp(name, "dcmap")) src = ms->dcmap;
+  for (int i = 0; i < 13 && !src; ++i)
+    if (!strcmp(name, kMapNames[i])) src = ms->maps[i];
+  if (!src) { g_err = std::string("fw25_mapset_read: unknown map '") + name + "'"; return 1; }
+  try {
+    MG_CUDA(cudaSetDevice(ms->device));
+    const int nC = ms->ndim == 3 ? ms->nZ : ms->nY;
+    const size_t rows = ms->ndim == 3 ? (size_t)ms->nX * ms->nY : (size_t)ms->nX;
+    MG_CUDA(cudaMemcpy2D(out, (size_t)nC * 4, src, (size_t)ms->pitch * 4, (size_t)nC * 4, rows, cudaMemcpyDeviceToHost));
+  } catch (const MgFail &f) {
+    return f.code;
+  }
+  return 0;
+}
+
+int64_t fw25_mapset_invalid_count(const fw25_mapset *ms) { return ms ? ms->invalid : -1; }
+
+void fw25_mapset_destroy(fw25_mapset *ms) { delete ms; }
+
+}  // extern "C"

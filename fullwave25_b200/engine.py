@@ -185,7 +185,7 @@ class Engine:
 
     def __init__(self, pb: Problem, device: int = 0, slab: tuple[int, int, int, int] | None = None,
                  device_maps: dict | None = None, ext_state: dict | None = None, variant: int = 0):
-        if device_maps is None:
+        if device_maps is None or pb.rho is None:
             pb.normalise()
         self.pb = pb
         s, self._keep = marshal(pb, device_maps=device_maps, ext_state=ext_state)

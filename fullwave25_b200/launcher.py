@@ -205,12 +205,64 @@ def install(fullwave_module=None):
     return uninstall
 
 
+def _whole_domain_sensor(solver, modulus: int):
+    import fullwave
+    eg = solver.pml_builder.extended_grid
+    shape = (eg.nx, eg.ny, eg.nz) if solver.is_3d else (eg.nx, eg.ny)
+    return fullwave.Sensor(mask=np.ones(shape, dtype=bool), sampling_modulus_time=modulus)
+
+
+def _run_solver_device_maps(solver, sensor, device: int, session: Session | None):
+    """The engine input without `PMLBuilder.run` and without any extended-grid array on the host: the thirteen
+    coefficient maps and dcmap are generated on the GPU from the solver's ORIGINAL (user-grid) medium
+    (`mapgen.MapSet`, fw25_mapgen) and adopted by the engine in place."""
+    from . import mapgen
+    pmlb = solver.pml_builder
+    t0 = time.perf_counter()
+    spec = mapgen.MediumSpec.from_pml_builder(pmlb, use_pml=solver.use_pml, dcmap_full3d=False)
+    ms = mapgen.MapSet(spec, device=device)
+    if ms.invalid_count:
+        logger.warning("Warning: Some attenuation values correspond to invalid relaxation parameters. "
+                       "This is due to the limitations of the precomputed lookup table. "
+                       "Please change the attenuation values.\nNumber of invalid points: %d.", ms.invalid_count)
+    # the reference's anisotropic binaries have no inject_source_zero kernel: they ignore the air map (fw25.h)
+    air = pmlb.extended_medium.air_map if getattr(solver, "use_isotropic_relaxation", True) else None
+    pb = Problem.for_device_maps(ms, pmlb.extended_grid, pmlb.extended_source, sensor, air_map=air)
+    eng = engine.Engine(pb, device=device, device_maps=ms.device_maps())
+    setup_s = time.perf_counter() - t0
+    try:
+        genout, stats = eng.run()
+    finally:
+        if session is None:
+            eng.close()
+            ms.close()
+    if session is not None:
+        session.eng, session.shape = eng, pb.shape
+    stats.update(mapgen_upload_ms=ms.upload_ms, mapgen_kernel_ms=ms.kernel_ms, host_setup_s=setup_s, maps="device")
+    return genout, stats, pb
+
+
 def run_solver(solver, *, record_whole_domain: bool = False, sampling_modulus_time_whole_domain: int = 1,
-               cuda_device_id=None, return_stats: bool = False, session: Session | None = None):
-    """`Solver.run` without the disk: PMLBuilder stays the reference's own Python (solver.py:694), the engine
-    input is assembled in memory (what InputFileWriter would have written, input_file_writer.py:563-881) and
-    the sensor traces come back as [n_sensors, n_frames] exactly like `Solver._reshape_sensor_data`."""
+               cuda_device_id=None, return_stats: bool = False, session: Session | None = None,
+               maps: str = "host"):
+    """`Solver.run` without the disk.  maps="host": PMLBuilder stays the reference's own Python (solver.py:694), the
+    engine input is assembled in memory (what InputFileWriter would have written, input_file_writer.py:563-881) --
+    bit-identical to the reference binary.  maps="device": the coefficient maps are built on the GPU from the
+    user-grid medium instead (fw25_mapgen; a / b within one float32 ulp of the reference's files, everything else
+    bit-identical; one device).  The sensor traces come back as [n_sensors, n_frames] exactly like
+    `Solver._reshape_sensor_data`."""
+    if maps not in ("host", "device"):
+        raise ValueError('maps must be "host" or "device"')
     ids = device_ids_of(cuda_device_id if cuda_device_id is not None else getattr(solver, "cuda_device_id", None))
+    if maps == "device" and len(ids) == 1 and not (session is not None and session.eng is not None):
+        sensor = (_whole_domain_sensor(solver, sampling_modulus_time_whole_domain) if record_whole_domain
+                  else solver.pml_builder.extended_sensor)
+        try:
+            genout, stats, pb = _run_solver_device_maps(solver, sensor, ids[0], session)
+        except engine.EngineError as e:
+            raise SimulationError(str(e)) from e
+        result = genout.reshape(-1, pb.ncoordsout).T
+        return (result, stats) if return_stats else result
     if session is not None and session.eng is not None:      # next transmit event: only the sources change
         src = solver.pml_builder.extended_source
         eg = solver.pml_builder.extended_grid
@@ -227,11 +279,7 @@ def run_solver(solver, *, record_whole_domain: bool = False, sampling_modulus_ti
     extended_medium = solver.pml_builder.run(use_pml=solver.use_pml)
     sensor = solver.pml_builder.extended_sensor
     if record_whole_domain:
-        import fullwave
-        eg = solver.pml_builder.extended_grid
-        shape = (eg.nx, eg.ny, eg.nz) if solver.is_3d else (eg.nx, eg.ny)
-        sensor = fullwave.Sensor(mask=np.ones(shape, dtype=bool),
-                                 sampling_modulus_time=sampling_modulus_time_whole_domain)
+        sensor = _whole_domain_sensor(solver, sampling_modulus_time_whole_domain)
     pb = Problem.from_fullwave_objects(solver.pml_builder.extended_grid, extended_medium,
                                        solver.pml_builder.extended_source, sensor)
     try:

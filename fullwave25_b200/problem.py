@@ -116,18 +116,21 @@ class Problem:
                     raise ValueError(f"{stem}: {a.size} values, grid has {self.n_points}")
                 self.aniso[stem] = a.reshape(self.shape)
         for name in MAP_NAMES:
+            if getattr(self, name) is None:      # maps resident on the device (mapgen.MapSet): nothing to cast
+                continue
             a = np.ascontiguousarray(getattr(self, name), dtype=np.float32)
             if a.size != self.n_points:
                 raise ValueError(f"{name}: {a.size} values, grid has {self.n_points}")
             setattr(self, name, a.reshape(self.shape))
-        self.dcmap = np.ascontiguousarray(self.dcmap, dtype=np.int32).reshape(self.shape)
+        if self.dcmap is not None:
+            self.dcmap = np.ascontiguousarray(self.dcmap, dtype=np.int32).reshape(self.shape)
         self.dmap = np.ascontiguousarray(self.dmap, dtype=np.float32).reshape(9, 2, -1)
         if self.dmap.shape[2] < self.ndmap:
             raise ValueError("dmap has fewer columns than ndmap")
         if self.dmap.shape[2] != self.ndmap:
             # the reference writes ndmap = 1 for a homogeneous medium; keep the columns the engine reads
             self.dmap = np.ascontiguousarray(self.dmap[:, :, : self.ndmap])
-        if self.dcmap.size and (self.dcmap.min() < 0 or self.dcmap.max() >= self.ndmap):
+        if self.dcmap is not None and self.dcmap.size and (self.dcmap.min() < 0 or self.dcmap.max() >= self.ndmap):
             raise ValueError("dcmap entries must lie in [0, ndmap)")
         self.icc = np.ascontiguousarray(self.icc, dtype=np.int32).reshape(-1, self.ndim)
         self.outc = np.ascontiguousarray(self.outc, dtype=np.int32).reshape(-1, self.ndim)
@@ -258,6 +261,29 @@ class Problem:
             icczero=np.stack(np.nonzero(air != 0), axis=1) if air.any() else np.zeros((0, c.ndim), np.int32),
             extra={"c": c, "d": d_tab, "dY": grid.dy, "dZ": getattr(grid, "dz", grid.dx), "c0": grid.c0},
             aniso=aniso,
+        )
+        return pb.normalise()
+
+    @classmethod
+    def for_device_maps(cls, mapset, grid, source, sensor, air_map=None) -> "Problem":
+        """Engine input whose 13 maps + dcmap already sit in HBM (`mapgen.MapSet`): only the step counts, the
+        stencil table and the source / sensor / air-voxel lists come from the host.  grid, source, sensor: the
+        reference's PML-extended objects (as in `from_fullwave_objects`); air_map: the extended air map."""
+        is_3d = len(mapset.shape) == 3
+        icmat = np.asarray(source.icmat)
+        nd = 3 if is_3d else 2
+        air = None if air_map is None else np.asarray(air_map)
+        none_maps = {name: None for name in MAP_NAMES}
+        pb = cls(
+            ndim=nd, nX=int(mapset.shape[0]), nY=int(mapset.shape[1]), nZ=int(mapset.shape[2]) if is_3d else 1,
+            nT=int(grid.nt), nTic=int(icmat.shape[1]), modT=int(sensor.sampling_modulus_time), ndmap=mapset.ndmap,
+            dX=float(np.float32(grid.dx)), dT=float(np.float32(grid.dt)), **none_maps,
+            dmap=mapset.dmap, dcmap=None,
+            icc=np.asarray(source.incoords), icmat=icmat, outc=np.asarray(sensor.outcoords),
+            icczero=(np.stack(np.nonzero(air != 0), axis=1) if air is not None and air.any()
+                     else np.zeros((0, nd), np.int32)),
+            extra={"d": mapset.d_table, "c0": getattr(grid, "c0", 1540.0)},
+            dcmap_full3d=True,       # a reference-style truncation is already inside the generated dcmap
         )
         return pb.normalise()
 

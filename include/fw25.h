@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define FW25_ABI_VERSION 4
+#define FW25_ABI_VERSION 5
 #define FW25_M 8 /* stencil half-width: solver.py:296 (m_spatial_order = 8), kernels launched with M = 8 */
 
 /* Anisotropic-relaxation file set (upstream `use_isotropic_relaxation=False`, input_file_writer.py:592-620; engine
@@ -158,6 +158,58 @@ int fw25_set_kernel_variant(fw25_engine *e, int32_t variant);
 /* number of CUDA devices visible to this process: the executable drop-in shards over all of them, like the
  * reference binary does with CUDA_VISIBLE_DEVICES (launcher.py:206; binary: cudaGetDeviceCount in main) */
 int32_t fw25_device_count(void);
+
+/* ---- Medium maps built ON THE GPU.  Upstream, every `Solver.run` first builds the engine's
+ * 13 coefficient maps on the host in float64 numpy: `PMLBuilder.__init__` pads the user-grid maps by edge
+ * replication (pml_builder.py:321-704), `PMLBuilder.run` ramps d / alpha of both relaxation mechanisms towards their
+ * PML targets axis by axis (`_apply_pml`, `_apply_pml_3d`, `_apply_transition_and_pml`, :842-1498), turns them into
+ * a, b (`_calc_a_and_b`, :794-810), and `InputFileWriter` derives K = c^2 rho, dcmap and casts everything to
+ * float32 (input_file_writer.py:95-103, :563-627, :716-745).  fw25_mapgen does all of that in one kernel, from the
+ * USER-grid float64 maps, straight into the engine's HBM layout -- same float64 operations in the same order, so
+ * rho, K, beta, kappa and dcmap are bit-identical to the reference's files and a, b agree to 1 float32 ulp (exp()).
+ * All pointers are HOST pointers to C-contiguous arrays over the user grid [nx][ny][nz] (nz = 1 in 2D). */
+typedef struct fw25_medium {
+  int32_t ndim;                      /* 2 or 3 */
+  int32_t nx, ny, nz;                /* USER grid (Medium.sound_speed.shape) */
+  int32_t m_spatial_order;           /* 8 (solver.py:296) */
+  int32_t n_pml_layer;               /* PMLBuilder.n_pml_layer        (solver.py:483-486: 3 * ppw) */
+  int32_t n_transition_layer;        /* PMLBuilder.n_transition_layer (same default) */
+  int32_t use_pml;                   /* 0: `PMLBuilder.run(use_pml=False)` -- pad only, no ramps (pml_builder.py:838-840) */
+  double dt;                         /* extended_grid.dt */
+  double d_target_pml;               /* pml_builder.py:1063-1070, a host scalar */
+  /* the reference's 1-D transition functions sampled by numpy on the host (pml_builder.py:1296-1338):
+   * polynomial (d, nu = 1) and linear (alpha, nu = 1) over n_pml + n_transition + 1 points, cosine (nu = 2) over
+   * n_transition + 1 points */
+  const double *tf_polynomial, *tf_linear, *tf_cosine;
+  const double *sound_speed, *density, *beta;
+  /* relaxation parameters in the reference's dictionary order (solver/utils.py:68-86):
+   * kappa_x1, kappa_x2, d_x1_nu1, alpha_x1_nu1, d_x2_nu1, alpha_x2_nu1, d_x1_nu2, alpha_x1_nu2, d_x2_nu2, alpha_x2_nu2
+   * (`MediumRelaxationMaps.relaxation_param_dict`).  All NULL: look them up per voxel from the table below, which is
+   * what `Medium.build()` does on the host (utils/relaxation_parameters.py:18-75, :189-242). */
+  const double *relax[10];
+  const double *alpha_coeff, *alpha_power;   /* user-grid maps for the look-up */
+  const double *lut;                         /* database [lut_na][lut_np][10] */
+  const double *lut_alpha, *lut_power;       /* alpha_0_list / power_list rounded to 10 decimals, ascending */
+  int32_t lut_na, lut_np;
+  double alpha_min, alpha_max, power_min, power_max;   /* clip bounds (relaxation_parameters.py:152-155, :216-217) */
+  const uint8_t *lut_invalid;                /* invalid_matrix [lut_na][lut_np] or NULL: counted, like the warning */
+  int32_t c_round_min;                       /* round(min(c) + 1e-9): dcmap = round(c + 1e-9) - c_round_min */
+  int32_t dcmap_full3d;                      /* as fw25_problem.dcmap_full3d: 0 zeroes dcmap beyond the first nX*nY entries */
+} fw25_medium;
+
+typedef struct fw25_mapset fw25_mapset; /* opaque: the 13 float maps + dcmap, device-resident, engine layout */
+
+/* Builds the maps on `device`.  stats_ms (may be NULL): [0] = host->device upload of the user-grid maps,
+ * [1] = the kernel (CUDA events). */
+int fw25_mapgen(const fw25_medium *md, int32_t device, fw25_mapset **out, double *stats_ms);
+/* Fills nX nY nZ (the EXTENDED grid), the 13 map pointers, dcmap, maps_on_device, map_pitch and dcmap_full3d of `pb`
+ * so that fw25_create adopts the maps without a copy.  The mapset must outlive every engine created from it. */
+int fw25_mapset_problem(const fw25_mapset *ms, fw25_problem *pb);
+/* name: a .dat stem ("rho", "K", "beta", "kappax", ..., "bpmlu2", "dcmap"); out: dense [nX][nY][nZ] float32 (int32
+ * for dcmap) on the host -- the bytes the reference would have written to <name>.dat. */
+int fw25_mapset_read(const fw25_mapset *ms, const char *name, void *out);
+int64_t fw25_mapset_invalid_count(const fw25_mapset *ms);   /* voxels that hit an invalid look-up entry */
+void fw25_mapset_destroy(fw25_mapset *ms);
 
 const char *fw25_last_error(void);
 int32_t fw25_abi_version(void);

@@ -105,6 +105,38 @@ def test_solver_run_identical_through_every_boundary(built_lib, shape):
 
 @needs_ref
 @pytest.mark.gpu
+@pytest.mark.parametrize("shape,iso", [((40, 48), True), ((20, 24, 28), True), ((18, 20, 22), False)])
+def test_run_solver_with_gpu_built_maps_matches_reference_binary(built_lib, shape, iso):
+    """`run_solver(solver, maps="device")`: PMLBuilder.run and the extended-grid host arrays are replaced by
+    fw25_mapgen.  a / b may differ from the reference's files by one float32 ulp (exp), so the traces are compared
+    with the north star's tolerance, relative L2 <= 1e-5, against the reference's own binary; whole-domain recording
+    and a transmit-event session ride on the same maps."""
+    fw, grid, medium, source, sensor = ref_objects.build(shape, n_steps=60, n_sensors=12, n_air=6, modT=3)
+    kw = dict(pml_layer_thickness_px=6, n_transition_layer=4, use_isotropic_relaxation=iso)
+    if not iso:
+        medium.use_isotropic_relaxation = False      # (else Solver logs a warning whose own format string is broken)
+    with tempfile.TemporaryDirectory() as td:
+        s_ref = fw.Solver(Path(td) / "ref", grid, medium, source, sensor,
+                          path_fullwave_simulation_bin=ref_objects.ref_bin(len(shape), isotropic=iso), **kw)
+        want = s_ref.run()
+        got, stats = launcher.run_solver(s_ref, maps="device", return_stats=True)
+        assert stats["maps"] == "device" and stats["mapgen_kernel_ms"] > 0
+        assert got.shape == want.shape and np.abs(want).max() > 0
+        rel = np.linalg.norm(got.astype(np.float64) - want) / np.linalg.norm(want.astype(np.float64))
+        assert rel <= 1e-5, rel
+        host = launcher.run_solver(s_ref, record_whole_domain=True, sampling_modulus_time_whole_domain=20)
+        dev = launcher.run_solver(s_ref, record_whole_domain=True, sampling_modulus_time_whole_domain=20, maps="device")
+        assert dev.shape == host.shape == (int(np.prod([n + 2 * 18 for n in shape])), 3)
+        assert np.linalg.norm(dev.astype(np.float64) - host) <= 1e-5 * np.linalg.norm(host.astype(np.float64))
+        with launcher.Session() as ses:
+            first = launcher.run_solver(s_ref, maps="device", session=ses)
+            again = launcher.run_solver(s_ref, maps="device", session=ses)     # maps stay resident, sources re-sent
+        np.testing.assert_array_equal(first, got)
+        np.testing.assert_array_equal(again, got)
+
+
+@needs_ref
+@pytest.mark.gpu
 @pytest.mark.parametrize("shape", [(40, 48), (20, 24, 28)])
 def test_static_map_transmit_events_reuse_device_maps(built_lib, shape):
     """The reference's multi-transmit loop -- a new Solver per event, run(is_static_map=True, recalculate_pml=k==0)
