@@ -17,6 +17,7 @@
 #include <string>
 #include <thread>
 #include <unordered_set>
+#include <numeric>
 #include <vector>
 
 #include "../../include/fw25.h"
@@ -49,6 +50,30 @@ static void fail(int code, const std::string &msg) {
 
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
+// Is the coordinate list exactly the points of a box in row-major order?  (A rectangular `Sensor(mask)`:
+// np.where order, sensor.py:24-50.)  box: lo[nd], hi[nd].
+static bool detect_box(const int32_t *c, int n, int nd, int32_t *box) {
+  long long vol = 1;
+  for (int k = 0; k < nd; ++k) {
+    box[k] = c[k];
+    box[nd + k] = c[(size_t)(n - 1) * nd + k] + 1;
+    if (box[nd + k] <= box[k]) return false;
+    vol *= box[nd + k] - box[k];
+  }
+  if (vol != n) return false;
+  int32_t cur[3] = {box[0], box[1], nd == 3 ? box[2] : 0};
+  for (int i = 0; i < n; ++i) {
+    const int32_t *ci = c + (size_t)i * nd;
+    for (int k = 0; k < nd; ++k)
+      if (ci[k] != cur[k]) return false;
+    for (int k = nd - 1; k >= 0; --k) {        // next point, last axis fastest
+      if (++cur[k] < box[nd + k]) break;
+      cur[k] = box[k];
+    }
+  }
+  return true;
+}
+
 struct Engine {
   int device = 0;
   int ndim = 3;
@@ -70,7 +95,10 @@ struct Engine {
   int n_air = 0;
   long long *d_sens_idx = nullptr;
   int n_sens = 0, n_sens_global = 0;
-  std::vector<int32_t> sens_ids;
+  std::vector<int32_t> sens_ids;             // global outc row of each local sensor (box sensors: filled on demand)
+  bool sens_box = false;                     // the sensors are every point of a box: no index list (fw25.h, out_box)
+  SensBox box{};
+  int sens_first = 0;                        // box sensors: global outc row of local sensor 0 (rows are contiguous)
   std::vector<void *> src_owned;             // source-list allocations (replaced by reset())
   std::unordered_set<long long> air_set;     // linear indices of the air voxels held locally
   float *d_frames = nullptr;
@@ -380,7 +408,33 @@ struct Engine {
       air_set.insert(idx.begin(), idx.end());
     }
     setup_sources(pb.ncoords, pb.icc, pb.icmat);
-    {  // sensors owned by this slab, in global outc order
+    int32_t found_box[6];
+    const int32_t *obox = pb.out_box;
+    if (!obox && pb.outc && pb.ncoordsout >= 4096 && detect_box(pb.outc, pb.ncoordsout, nd, found_box)) obox = found_box;
+    if (obox) {  // box sensors: the owned planes of the box are a contiguous run of global outc rows
+      const int dims[3] = {nX_global, nY, nZ};
+      long long vol = 1, per_plane = 1;
+      for (int k = 0; k < nd; ++k) {
+        if (obox[k] < 0 || obox[nd + k] > dims[k] || obox[k] > obox[nd + k]) fail(1, "out_box: box outside the grid");
+        vol *= obox[nd + k] - obox[k];
+        if (k > 0) per_plane *= obox[nd + k] - obox[k];
+      }
+      if (vol != pb.ncoordsout) fail(1, "out_box: ncoordsout is not the box volume");
+      const int x0 = std::max(obox[0], own_lo), x1 = std::min(obox[nd], own_hi);
+      sens_box = true;
+      box.wa = vol > 0 ? std::max(x1 - x0, 0) : 0;
+      box.a0 = x0 - gx0;
+      box.b0 = nd == 3 ? obox[1] : 0;            box.wb = nd == 3 ? obox[4] - obox[1] : 1;
+      box.c0 = nd == 3 ? obox[2] : obox[1];      box.wc = nd == 3 ? obox[5] - obox[2] : obox[3] - obox[1];
+      box.a_lo = M - gx0;                        box.a_hi = nX_global - M - gx0;
+      box.b_lo = nd == 3 ? M : 0;                box.b_hi = nd == 3 ? nY - M : 1;
+      box.c_lo = M;                              box.c_hi = G.nC - M;
+      box.sA = G.sA; box.sB = G.sB;
+      if ((long long)box.wa * per_plane > INT32_MAX || box.wb > 65535 || box.wa > 65535) fail(1, "out_box: box too large");
+      n_sens = (int)((long long)box.wa * per_plane);
+      sens_first = (int)((long long)(x0 - obox[0]) * per_plane);
+      d_sens_idx = nullptr;
+    } else {  // sensors owned by this slab, in global outc order
       std::vector<long long> idx;
       if (pb.ncoordsout > 0 && !pb.outc) fail(1, "outc pointer is NULL");
       for (int i = 0; i < pb.ncoordsout; ++i) {
@@ -454,8 +508,18 @@ struct Engine {
   }
   void record(int frame, cudaStream_t st) {
     if (n_sens == 0) return;
-    launch_record(F.p, d_sens_idx, n_sens, d_frames + (size_t)(frame % frames_cap) * n_sens, st);
+    float *slot = d_frames + (size_t)(frame % frames_cap) * n_sens;
+    if (sens_box) launch_record_box(F.p, slot, n_sens, nullptr, 0, 1, 1, box, st);
+    else launch_record(F.p, d_sens_idx, n_sens, slot, st);
     launches += 1;
+  }
+  // global outc rows of the local sensors; box sensors keep only the first row until somebody asks
+  const std::vector<int32_t> &sensor_ids() {
+    if (sens_box && (int)sens_ids.size() != n_sens) {
+      sens_ids.resize(n_sens);
+      std::iota(sens_ids.begin(), sens_ids.end(), sens_first);
+    }
+    return sens_ids;
   }
   void step_once() {
     inject(t, stream);
@@ -488,7 +552,8 @@ struct Engine {
       sweep_u(0, nX_global, stream);
       sweep_p(0, nX_global, stream);
       if (sg.records && j % modT == 0 && n_sens > 0) {
-        launch_record_dev(F.p, d_sens_idx, n_sens, d_frames, d_t, j, modT, frames_cap, stream);
+        if (sens_box) launch_record_box(F.p, d_frames, n_sens, d_t, j, modT, frames_cap, box, stream);
+        else launch_record_dev(F.p, d_sens_idx, n_sens, d_frames, d_t, j, modT, frames_cap, stream);
         ++launches;
       }
       if (sg.records && j % modT == 0) ++sg.frames;
@@ -591,6 +656,10 @@ void scatter_frames(Engine &e, int f0, int f1, float *genout, int ncoordsout, st
   for (int f = f0; f < f1; ++f) {
     const float *src = tmp.data() + (size_t)(f - f0) * e.n_sens;
     float *dst = genout + (size_t)f * ncoordsout;
+    if (e.sens_box) {                        // a slab's share of a box is one contiguous run of rows
+      memcpy(dst + e.sens_first, src, (size_t)e.n_sens * sizeof(float));
+      continue;
+    }
     for (int i = 0; i < e.n_sens; ++i) dst[e.sens_ids[i]] = src[i];
   }
 }
@@ -1178,7 +1247,8 @@ int fw25_sync(fw25_engine *h) {
 
 int32_t fw25_n_local_sensors(const fw25_engine *h) { return h->e.n_sens; }
 int fw25_local_sensor_ids(const fw25_engine *h, int32_t *ids) {
-  std::copy(h->e.sens_ids.begin(), h->e.sens_ids.end(), ids);
+  const std::vector<int32_t> &v = const_cast<fw25_engine *>(h)->e.sensor_ids();
+  std::copy(v.begin(), v.end(), ids);
   return 0;
 }
 int fw25_read_frames(fw25_engine *h, int32_t f0, int32_t f1, float *out) {

@@ -49,6 +49,15 @@ void launch_record(const float *p, const long long *sens_idx, int n_sens, float 
 // graph-replayed forms: the step number is *d_t + t_off (device-side counter, advanced by launch_tick)
 void launch_record_dev(const float *p, const long long *sens_idx, int n_sens, float *frames, const int *d_t, int t_off,
                        int modT, int cap, cudaStream_t st);
+// box sensors: local origin (a0, b0, c0) and extent (wa, wb, wc) of the owned part of the box in the engine's layout,
+// the local index ranges outside which a point lies in the never-updated rim (reads 0), array strides
+struct SensBox {
+  int a0, b0, c0, wa, wb, wc;
+  int a_lo, a_hi, b_lo, b_hi, c_lo, c_hi;
+  long long sA, sB;
+};
+void launch_record_box(const float *p, float *frames, long long n_sens, const int *d_t, int t_off, int modT, int cap,
+                       const SensBox &B, cudaStream_t st);
 void launch_tick(int *d_t, int set, int add, cudaStream_t st);   // *d_t = (set >= 0 ? set : *d_t) + add
 int launches_per_inject(int n_src, int n_air, int t, int nTic, int n_src_rim);
 

@@ -50,6 +50,20 @@ __global__ void k_record_dev(const float *__restrict__ p, const long long *__res
   frames[(size_t)f * n_sens + i] = s < 0 ? 0.0f : p[s];
 }
 
+// Box sensors (every point of a box, row-major: rectangular sensor masks, whole-domain recording): no index list,
+// one thread per box point, lanes along the contiguous axis; 4 B read + 4 B written per point instead of 16.
+// frame slot: `frames` itself, or ((*d_t + t_off) / modT) % cap when the step number lives on the device.
+__global__ void k_record_box(const float *__restrict__ p, float *__restrict__ frames, long long n_sens,
+                             const int *__restrict__ d_t, int t_off, int modT, int cap, SensBox B) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= B.wc) return;
+  const int b = blockIdx.y, a = blockIdx.z;
+  float *frame = d_t ? frames + (size_t)(((*d_t + t_off) / modT) % cap) * n_sens : frames;
+  const int la = B.a0 + a, lb = B.b0 + b, lc = B.c0 + c;          // local plane, row, column
+  const bool rim = la < B.a_lo || la >= B.a_hi || lb < B.b_lo || lb >= B.b_hi || lc < B.c_lo || lc >= B.c_hi;
+  frame[((size_t)a * B.wb + b) * B.wc + c] = rim ? 0.0f : p[(long long)la * B.sA + (long long)lb * B.sB + lc];
+}
+
 __global__ void k_tick(int *d_t, int set, int add) { *d_t = (set >= 0 ? set : *d_t) + add; }
 
 // Reference 3D behaviour (include/fw25.h, dcmap_full3d): entries whose flat index in the WHOLE dense grid
@@ -94,6 +108,13 @@ void launch_record_dev(const float *p, const long long *sens_idx, int n_sens, fl
                        int modT, int cap, cudaStream_t st) {
   if (n_sens > 0)
     k_record_dev<<<(n_sens + 255) / 256, 256, 0, st>>>(p, sens_idx, n_sens, frames, d_t, t_off, modT, cap);
+}
+
+void launch_record_box(const float *p, float *frames, long long n_sens, const int *d_t, int t_off, int modT, int cap,
+                       const SensBox &B, cudaStream_t st) {
+  if (n_sens <= 0) return;
+  dim3 grid((B.wc + 255) / 256, B.wb, B.wa);
+  k_record_box<<<grid, 256, 0, st>>>(p, frames, n_sens, d_t, t_off, modT, cap, B);
 }
 
 void launch_tick(int *d_t, int set, int add, cudaStream_t st) { k_tick<<<1, 1, 0, st>>>(d_t, set, add); }

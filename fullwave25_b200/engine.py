@@ -46,6 +46,7 @@ class CProblem(C.Structure):
         ("maps_on_device", C.c_int32), ("map_pitch", C.c_int32), ("dcmap_full3d", C.c_int32),
         ("ext_p", C.c_void_p), ("ext_u", C.c_void_p), ("ext_v", C.c_void_p), ("ext_w", C.c_void_p),
         ("aniso", C.POINTER(CAniso)),
+        ("out_box", C.c_void_p),
     ]
 
 
@@ -142,6 +143,10 @@ def marshal(pb: Problem, *, device_maps: dict | None = None, ext_state: dict | N
     s.dmap = pb.dmap.ctypes.data
     s.ncoords, s.icc, s.icmat = pb.ncoords, pb.icc.ctypes.data, pb.icmat.ctypes.data
     s.ncoordsout, s.outc = pb.ncoordsout, pb.outc.ctypes.data
+    if pb.out_box is not None:          # box sensors: no coordinate list at all
+        box = np.asarray(pb.out_box, np.int32).reshape(2 * pb.ndim)
+        keep.append(box)
+        s.out_box, s.outc = box.ctypes.data, None
     s.ncoordszero, s.icczero = pb.ncoordszero, pb.icczero.ctypes.data
     if ext_state:
         s.ext_p, s.ext_u = ext_state.get("p"), ext_state.get("u")

@@ -205,14 +205,19 @@ def install(fullwave_module=None):
     return uninstall
 
 
-def _whole_domain_sensor(solver, modulus: int):
-    import fullwave
+def _sensor_and_box(solver, record_whole_domain: bool, modulus: int):
+    """(sensor, out_box).  `record_whole_domain` (solver.py:709-731) upstream builds a `Sensor` whose mask is the whole
+    extended grid -- one coordinate row per grid point.  Here it is a box (fw25.h, out_box): no mask, no coordinate
+    list on the host, no index list on the device; the frames come back in the same row-major order."""
+    if not record_whole_domain:
+        return solver.pml_builder.extended_sensor, None
+    from types import SimpleNamespace
     eg = solver.pml_builder.extended_grid
-    shape = (eg.nx, eg.ny, eg.nz) if solver.is_3d else (eg.nx, eg.ny)
-    return fullwave.Sensor(mask=np.ones(shape, dtype=bool), sampling_modulus_time=modulus)
+    shape = (int(eg.nx), int(eg.ny), int(eg.nz)) if solver.is_3d else (int(eg.nx), int(eg.ny))
+    return SimpleNamespace(sampling_modulus_time=int(modulus), outcoords=None), (0,) * len(shape) + shape
 
 
-def _run_solver_device_maps(solver, sensor, device: int, session: Session | None):
+def _run_solver_device_maps(solver, sensor, out_box, device: int, session: Session | None):
     """The engine input without `PMLBuilder.run` and without any extended-grid array on the host: the thirteen
     coefficient maps and dcmap are generated on the GPU from the solver's ORIGINAL (user-grid) medium
     (`mapgen.MapSet`, fw25_mapgen) and adopted by the engine in place."""
@@ -227,7 +232,7 @@ def _run_solver_device_maps(solver, sensor, device: int, session: Session | None
                        "Please change the attenuation values.\nNumber of invalid points: %d.", ms.invalid_count)
     # the reference's anisotropic binaries have no inject_source_zero kernel: they ignore the air map (fw25.h)
     air = pmlb.extended_medium.air_map if getattr(solver, "use_isotropic_relaxation", True) else None
-    pb = Problem.for_device_maps(ms, pmlb.extended_grid, pmlb.extended_source, sensor, air_map=air)
+    pb = Problem.for_device_maps(ms, pmlb.extended_grid, pmlb.extended_source, sensor, air_map=air, out_box=out_box)
     eng = engine.Engine(pb, device=device, device_maps=ms.device_maps())
     setup_s = time.perf_counter() - t0
     try:
@@ -255,10 +260,9 @@ def run_solver(solver, *, record_whole_domain: bool = False, sampling_modulus_ti
         raise ValueError('maps must be "host" or "device"')
     ids = device_ids_of(cuda_device_id if cuda_device_id is not None else getattr(solver, "cuda_device_id", None))
     if maps == "device" and len(ids) == 1 and not (session is not None and session.eng is not None):
-        sensor = (_whole_domain_sensor(solver, sampling_modulus_time_whole_domain) if record_whole_domain
-                  else solver.pml_builder.extended_sensor)
+        sensor, out_box = _sensor_and_box(solver, record_whole_domain, sampling_modulus_time_whole_domain)
         try:
-            genout, stats, pb = _run_solver_device_maps(solver, sensor, ids[0], session)
+            genout, stats, pb = _run_solver_device_maps(solver, sensor, out_box, ids[0], session)
         except engine.EngineError as e:
             raise SimulationError(str(e)) from e
         result = genout.reshape(-1, pb.ncoordsout).T
@@ -277,11 +281,9 @@ def run_solver(solver, *, record_whole_domain: bool = False, sampling_modulus_ti
         result = genout.reshape(-1, session.eng.pb.ncoordsout).T
         return (result, stats) if return_stats else result
     extended_medium = solver.pml_builder.run(use_pml=solver.use_pml)
-    sensor = solver.pml_builder.extended_sensor
-    if record_whole_domain:
-        sensor = _whole_domain_sensor(solver, sampling_modulus_time_whole_domain)
+    sensor, out_box = _sensor_and_box(solver, record_whole_domain, sampling_modulus_time_whole_domain)
     pb = Problem.from_fullwave_objects(solver.pml_builder.extended_grid, extended_medium,
-                                       solver.pml_builder.extended_source, sensor)
+                                       solver.pml_builder.extended_source, sensor, out_box=out_box)
     try:
         if session is not None and len(ids) == 1:
             session.eng = engine.Engine(pb, device=ids[0])

@@ -67,6 +67,9 @@ class Problem:
     # {file stem: map} for kappa{x,y[,z]}, kappa{u,w[,v]}, apml/bpml{x,y[,z],u,w[,v]}{1,2}.  None = isotropic.
     # When set, the isotropic fields kappax .. bpmlu2 above hold the x-axis members (kappax, kappau, apmlx*, apmlu*).
     aniso: dict | None = None
+    # Box sensors (include/fw25.h, out_box): (lo..., hi...) of a box whose every point is a sensor, row-major -- a
+    # rectangular `Sensor(mask)` or `record_whole_domain`.  outc is then unused (may be an empty list).
+    out_box: tuple | None = None
 
     # ------------------------------------------------------------------ basics
     @property
@@ -83,7 +86,18 @@ class Problem:
 
     @property
     def ncoordsout(self) -> int:
+        if self.out_box is not None:
+            b = np.asarray(self.out_box, np.int64).reshape(2, self.ndim)
+            return int(np.prod(b[1] - b[0]))
         return int(self.outc.shape[0])
+
+    def sensor_coords(self) -> np.ndarray:
+        """int32 [ncoordsout, ndim]: outc, or the box's points in row-major order."""
+        if self.out_box is None:
+            return self.outc
+        b = np.asarray(self.out_box, np.int64).reshape(2, self.ndim)
+        grids = np.meshgrid(*[np.arange(lo, hi) for lo, hi in zip(b[0], b[1])], indexing="ij")
+        return np.stack([g.reshape(-1) for g in grids], axis=1).astype(np.int32)
 
     @property
     def ncoordszero(self) -> int:
@@ -133,6 +147,11 @@ class Problem:
         if self.dcmap is not None and self.dcmap.size and (self.dcmap.min() < 0 or self.dcmap.max() >= self.ndmap):
             raise ValueError("dcmap entries must lie in [0, ndmap)")
         self.icc = np.ascontiguousarray(self.icc, dtype=np.int32).reshape(-1, self.ndim)
+        if self.out_box is not None:
+            self.out_box = tuple(int(v) for v in np.asarray(self.out_box).reshape(-1))
+            if len(self.out_box) != 2 * self.ndim:
+                raise ValueError("out_box must be (lo..., hi...) with 2 * ndim entries")
+            self.outc = np.zeros((0, self.ndim), np.int32)
         self.outc = np.ascontiguousarray(self.outc, dtype=np.int32).reshape(-1, self.ndim)
         self.icczero = np.ascontiguousarray(self.icczero, dtype=np.int32).reshape(-1, self.ndim)
         self.icmat = np.ascontiguousarray(self.icmat, dtype=np.float32).reshape(
@@ -215,7 +234,7 @@ class Problem:
         self.dmap.astype(np.float32).tofile(d / "dmap.dat")
         self.dcmap.astype(np.int32).tofile(d / "dcmap.dat")
         self.icc.astype(np.int32).tofile(d / "icc.dat")
-        self.outc.astype(np.int32).tofile(d / "outc.dat")
+        self.sensor_coords().astype(np.int32).tofile(d / "outc.dat")
         self.icczero.astype(np.int32).tofile(d / "icczero.dat")
         self.icmat.astype(np.float32).tofile(d / "icmat.dat")
         ints = {"nX": self.nX, "nY": self.nY, "nT": self.nT, "ncoords": self.ncoords,
@@ -233,7 +252,7 @@ class Problem:
 
     # ------------------------------------------------------------------ reference Python objects
     @classmethod
-    def from_fullwave_objects(cls, grid, medium, source, sensor) -> "Problem":
+    def from_fullwave_objects(cls, grid, medium, source, sensor, out_box=None) -> "Problem":
         """Build the engine input from the reference's (already PML-extended) objects, i.e. what
         ``InputFileWriter(...).run`` would write (input_file_writer.py:95-103, :150-153, :563-627,
         :753-821), without touching the disk.  Duck-typed: needs grid.{nx,ny,nz,nt,dx,dy,dz,dt,c0,cfl,is_3d},
@@ -257,15 +276,15 @@ class Problem:
             rho=medium.density, K=medium.bulk_modulus, beta=medium.beta, **maps,
             dmap=dmap, dcmap=dcmap,
             icc=np.asarray(source.incoords), icmat=icmat,
-            outc=np.asarray(sensor.outcoords),
+            outc=np.zeros((0, c.ndim), np.int32) if out_box is not None else np.asarray(sensor.outcoords),
             icczero=np.stack(np.nonzero(air != 0), axis=1) if air.any() else np.zeros((0, c.ndim), np.int32),
             extra={"c": c, "d": d_tab, "dY": grid.dy, "dZ": getattr(grid, "dz", grid.dx), "c0": grid.c0},
-            aniso=aniso,
+            aniso=aniso, out_box=out_box,
         )
         return pb.normalise()
 
     @classmethod
-    def for_device_maps(cls, mapset, grid, source, sensor, air_map=None) -> "Problem":
+    def for_device_maps(cls, mapset, grid, source, sensor, air_map=None, out_box=None) -> "Problem":
         """Engine input whose 13 maps + dcmap already sit in HBM (`mapgen.MapSet`): only the step counts, the
         stencil table and the source / sensor / air-voxel lists come from the host.  grid, source, sensor: the
         reference's PML-extended objects (as in `from_fullwave_objects`); air_map: the extended air map."""
@@ -279,11 +298,13 @@ class Problem:
             nT=int(grid.nt), nTic=int(icmat.shape[1]), modT=int(sensor.sampling_modulus_time), ndmap=mapset.ndmap,
             dX=float(np.float32(grid.dx)), dT=float(np.float32(grid.dt)), **none_maps,
             dmap=mapset.dmap, dcmap=None,
-            icc=np.asarray(source.incoords), icmat=icmat, outc=np.asarray(sensor.outcoords),
+            icc=np.asarray(source.incoords), icmat=icmat,
+            outc=np.zeros((0, nd), np.int32) if out_box is not None else np.asarray(sensor.outcoords),
             icczero=(np.stack(np.nonzero(air != 0), axis=1) if air is not None and air.any()
                      else np.zeros((0, nd), np.int32)),
             extra={"d": mapset.d_table, "c0": getattr(grid, "c0", 1540.0)},
             dcmap_full3d=True,       # a reference-style truncation is already inside the generated dcmap
+            out_box=out_box,
         )
         return pb.normalise()
 
@@ -296,4 +317,4 @@ class Problem:
         return Problem(ndim=self.ndim, nX=gx1 - gx0, nY=self.nY, nZ=self.nZ, nT=self.nT, nTic=self.nTic,
                        modT=self.modT, ndmap=self.ndmap, dX=self.dX, dT=self.dT, **kw, dmap=self.dmap,
                        dcmap=self.dcmap[gx0:gx1], icc=self.icc, icmat=self.icmat, outc=self.outc,
-                       icczero=self.icczero, extra={}, dcmap_full3d=self.dcmap_full3d)
+                       icczero=self.icczero, extra={}, dcmap_full3d=self.dcmap_full3d, out_box=self.out_box)

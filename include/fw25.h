@@ -76,6 +76,13 @@ typedef struct fw25_problem {
                                  inject_source_zero kernel -- so are the air voxels (icczero).  When every axis holds
                                  identical values (what the reference's own Python layer writes, pml_builder.py:
                                  896-1005) the engine runs its isotropic kernels on one copy. */
+  const int32_t *out_box;     /* optional (HOST pointer, 2*ndim ints: lo[ndim], hi[ndim]): the sensors are EVERY point
+                                 of the box [lo, hi), in row-major order -- what a rectangular `Sensor(mask)` yields
+                                 (sensor.py:24-50: np.where order) and what `Solver.run(record_whole_domain=True)` asks
+                                 for (solver.py:709-731, the whole extended grid).  outc may then be NULL and
+                                 ncoordsout must equal the box volume; frames come back in the same global order.
+                                 The engine records such sensors without an index list, and
+                                 recognises a box by itself in any outc list of >= 4096 coordinates. */
 } fw25_problem;
 
 /* x-slab owned by one engine when the grid is sharded along x (the reference's slab partitioner,

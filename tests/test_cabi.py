@@ -35,8 +35,8 @@ def test_python_binding_covers_the_header(built_lib):
 
 
 def test_struct_layout_matches_header(built_lib):
-    # 8 int32 + 2 float, 15 pointers, 3 x (int32 + pad + pointers), 3 int32 + pad, 4 pointers
-    assert ctypes.sizeof(engine.CProblem) == 8 * 4 + 2 * 4 + 15 * 8 + (8 + 16) + (8 + 8) + (8 + 8) + 16 + 32 + 8
+    # 8 int32 + 2 float, 15 pointers, 3 x (int32 + pad + pointers), 3 int32 + pad, 4 pointers, aniso, out_box
+    assert ctypes.sizeof(engine.CProblem) == 8 * 4 + 2 * 4 + 15 * 8 + (8 + 16) + (8 + 8) + (8 + 8) + 16 + 32 + 8 + 8
     assert ctypes.sizeof(engine.CAniso) == 2 * (3 + 6 + 6) * 8
     assert ctypes.sizeof(engine.CSlab) == 16
     assert ctypes.sizeof(engine.CStats) == 8 * 8 + 2 * 4

@@ -124,7 +124,9 @@ def test_run_solver_with_gpu_built_maps_matches_reference_binary(built_lib, shap
         assert got.shape == want.shape and np.abs(want).max() > 0
         rel = np.linalg.norm(got.astype(np.float64) - want) / np.linalg.norm(want.astype(np.float64))
         assert rel <= 1e-5, rel
+        ref_wd = s_ref.run(record_whole_domain=True, sampling_modulus_time_whole_domain=20)    # the reference binary
         host = launcher.run_solver(s_ref, record_whole_domain=True, sampling_modulus_time_whole_domain=20)
+        np.testing.assert_array_equal(host, ref_wd)          # box recording == the reference's whole-grid sensor list
         dev = launcher.run_solver(s_ref, record_whole_domain=True, sampling_modulus_time_whole_domain=20, maps="device")
         assert dev.shape == host.shape == (int(np.prod([n + 2 * 18 for n in shape])), 3)
         assert np.linalg.norm(dev.astype(np.float64) - host) <= 1e-5 * np.linalg.norm(host.astype(np.float64))
