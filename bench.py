@@ -115,10 +115,10 @@ def cpu_baseline(seconds: float = 12.0) -> dict:
 def host_setup_baseline() -> dict | None:
     """Host-side medium / relaxation setup of the REFERENCE (PMLBuilder.run + InputFileWriter stencil tables,
     solver.py:693-743) timed on this box's cores on a bounded grid -- BASELINE.json asks for it beside the
-    engine numbers.  None when baseline/_ref is not importable."""
+    engine numbers -- with the GPU map builder (fw25_mapgen) on the same grid next to it."""
     try:
         from tools import ref_objects
-        return ref_objects.time_host_setup((40, 64, 64))
+        return ref_objects.time_host_setup((40, 64, 64), gpu=True)
     except Exception as e:  # noqa: BLE001
         return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
 

@@ -86,7 +86,7 @@ def ref_bin(ndim: int, isotropic: bool = True) -> Path:
     raise FileNotFoundError("reference sm_100 executable not found (run tools/install_reference.sh)")
 
 
-def time_host_setup(user_shape, **kw) -> dict:
+def time_host_setup(user_shape, gpu: bool = False, **kw) -> dict:
     """Wall time of the reference's host-side setup for one run on this box's cores: PMLBuilder (pads the maps,
     builds the a/b/kappa PML maps; solver.py:527-536 + :694) and InputFileWriter's stencil tables
     (solver.py:734-743) -- everything `Solver.run` does before it touches the disk or the GPU."""
@@ -108,10 +108,22 @@ def time_host_setup(user_shape, **kw) -> dict:
     eg = pml.extended_grid
     ext = tuple(int(getattr(eg, a)) for a in ("nx", "ny", "nz")[: len(user_shape)])
     pts = int(np.prod(ext))
-    return {"what": "reference PMLBuilder.__init__+run and InputFileWriter.__init__ (numpy, float64)",
-            "user_grid": list(user_shape), "extended_grid": list(ext), "pml_builder_s": t1 - t0,
-            "stencil_tables_s": t2 - t1, "Mpoints_per_s": pts / (t2 - t0) / 1e6, "cores": os.cpu_count(),
-            "threads_used": 1}
+    out = {"what": "reference PMLBuilder.__init__+run and InputFileWriter.__init__ (numpy, float64)",
+           "user_grid": list(user_shape), "extended_grid": list(ext), "pml_builder_s": t1 - t0,
+           "stencil_tables_s": t2 - t1, "Mpoints_per_s": pts / (t2 - t0) / 1e6, "cores": os.cpu_count(),
+           "threads_used": 1}
+    if gpu:   # the same maps + stencil tables from fw25_mapgen (user-grid upload + one kernel), same box
+        from fullwave25_b200 import mapgen
+        mapgen.MapSet(mapgen.MediumSpec.from_pml_builder(pml)).close()          # warm-up: context, allocator
+        t3 = time.perf_counter()
+        ms = mapgen.MapSet(mapgen.MediumSpec.from_pml_builder(pml))
+        t4 = time.perf_counter()
+        out["gpu_mapgen"] = {"what": "fullwave25_b200.mapgen.MapSet: the 13 maps + dcmap + stencil tables, in HBM",
+                             "total_s": t4 - t3, "upload_ms": ms.upload_ms, "kernel_ms": ms.kernel_ms,
+                             "Mpoints_per_s": pts / (t4 - t3) / 1e6,
+                             "speedup_vs_host": (t2 - t0) / (t4 - t3)}
+        ms.close()
+    return out
 
 
 if __name__ == "__main__":
