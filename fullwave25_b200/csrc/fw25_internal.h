@@ -6,6 +6,23 @@
 
 namespace fw25 {
 
+// Launch with programmatic stream serialization (PDL): inside a stream capture this becomes a programmatic edge of the
+// graph.  Only for kernels written for it (pdl_wait() before the first dependent access, fw25_kernels.cuh).
+// FW25_PDL=0 turns the attribute off (plain serialization) for A/B runs.
+bool pdl_enabled();
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args &&...args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // simple (L1/L2-cached) sweeps: fw25_sweeps_simple.cu.  a_lo/a_hi are LOCAL plane indices.
 // aniso: read the per-axis maps (Fields::kv .. bp) instead of the per-sweep ones
 void launch_sweep_u_simple(int ndim, const Fields &F, const Geom &G, int a_lo, int a_hi, cudaStream_t st, bool aniso = false);

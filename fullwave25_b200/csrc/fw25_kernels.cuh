@@ -28,6 +28,15 @@ __device__ __forceinline__ float div_(float a, float b) {
 }
 __device__ __forceinline__ float rcp_(float a) { return __frcp_rn(a); }
 
+// Programmatic dependent launch (griddepcontrol): a kernel launched with the programmatic-serialization attribute
+// (launch_pdl, fw25_internal.h) may start while its predecessor in the stream / graph is still running.  It must not
+// touch anything the predecessor writes -- or write anything the predecessor reads -- before pdl_wait(), which
+// returns once the predecessor grid has completed and its memory operations are visible.  Every thread that does
+// work calls pdl_wait(), so completion is transitive along a chain of such kernels.  pdl_trigger() lets the
+// successor be scheduled as soon as every CTA of this grid has started.  Both are no-ops for plain launches.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // Internal layout: every field is [nA][nB][pitch] float32, C (fastest) axis padded to `pitch`
 // (multiple of 4 floats => 16-byte aligned rows for float4 / TMA).  3D: (A,B,C) = (x,y,z).
 // 2D: (A,B,C) = (x,-,y) with nB = 1, i.e. the reference's 2D "y" is our C axis; its v / *y* arrays

@@ -4,10 +4,19 @@
 // linear-index maps are resolved once at setup (bit-exact int arithmetic on the host), so the per-step
 // kernels are pure scatter / gather; injection and zeroing share one launch.
 #include <algorithm>
+#include <cstdlib>
 
 #include "fw25_internal.h"
 
 namespace fw25 {
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char *e = getenv("FW25_PDL");
+    return !e || atoi(e) != 0;
+  }();
+  return on;
+}
 
 // p[src] = icmat[row][t] while t < nTic (overwrite, not add); afterwards a source that sits in the
 // never-updated 8-cell rim falls back to 0 (the reference's proceed_time copies the zero new half
@@ -19,34 +28,44 @@ __global__ void k_inject(float *__restrict__ p, const long long *__restrict__ sr
                          const int *__restrict__ src_row, const unsigned char *__restrict__ src_flag,
                          int n_src, const float *__restrict__ icmat, int nTic, int t_off,
                          const int *__restrict__ d_t, const long long *__restrict__ air_idx, int n_air) {
+  pdl_trigger();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_src) {
+    const unsigned char f = src_flag[i];                 // index lists are written at setup only
+    const long long s = src_idx[i];
+    const int row = src_row[i];
+    pdl_wait();                                          // p belongs to the previous kernel until here; d_t to k_tick
     const int t = d_t ? *d_t + t_off : t_off;
-    const unsigned char f = src_flag[i];
     if (f & 2) return;
-    if (t < nTic) p[src_idx[i]] = icmat[(size_t)src_row[i] * nTic + t];
-    else if (f & 1) p[src_idx[i]] = 0.0f;
+    if (t < nTic) p[s] = icmat[(size_t)row * nTic + t];
+    else if (f & 1) p[s] = 0.0f;
   } else if (i < n_src + n_air) {
-    p[air_idx[i - n_src]] = 0.0f;
+    const long long s = air_idx[i - n_src];
+    pdl_wait();
+    p[s] = 0.0f;
   }
 }
 
 // frame[i] = p'[sensor_i]; sensors in the 8-cell rim (idx < 0) read 0.
 __global__ void k_record(const float *__restrict__ p, const long long *__restrict__ sens_idx, int n_sens,
                          float *__restrict__ frame) {
+  pdl_trigger();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_sens) return;
   const long long s = sens_idx[i];
+  pdl_wait();
   frame[i] = s < 0 ? 0.0f : p[s];
 }
 
 // graph-replayed form: the frame slot comes from the device-side step counter, frame = ((*d_t + t_off) / modT) % cap
 __global__ void k_record_dev(const float *__restrict__ p, const long long *__restrict__ sens_idx, int n_sens,
                              float *__restrict__ frames, const int *__restrict__ d_t, int t_off, int modT, int cap) {
+  pdl_trigger();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_sens) return;
-  const int f = ((*d_t + t_off) / modT) % cap;
   const long long s = sens_idx[i];
+  pdl_wait();
+  const int f = ((*d_t + t_off) / modT) % cap;
   frames[(size_t)f * n_sens + i] = s < 0 ? 0.0f : p[s];
 }
 
@@ -55,16 +74,22 @@ __global__ void k_record_dev(const float *__restrict__ p, const long long *__res
 // frame slot: `frames` itself, or ((*d_t + t_off) / modT) % cap when the step number lives on the device.
 __global__ void k_record_box(const float *__restrict__ p, float *__restrict__ frames, long long n_sens,
                              const int *__restrict__ d_t, int t_off, int modT, int cap, SensBox B) {
+  pdl_trigger();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= B.wc) return;
   const int b = blockIdx.y, a = blockIdx.z;
+  pdl_wait();
   float *frame = d_t ? frames + (size_t)(((*d_t + t_off) / modT) % cap) * n_sens : frames;
   const int la = B.a0 + a, lb = B.b0 + b, lc = B.c0 + c;          // local plane, row, column
   const bool rim = la < B.a_lo || la >= B.a_hi || lb < B.b_lo || lb >= B.b_hi || lc < B.c_lo || lc >= B.c_hi;
   frame[((size_t)a * B.wb + b) * B.wc + c] = rim ? 0.0f : p[(long long)la * B.sA + (long long)lb * B.sB + lc];
 }
 
-__global__ void k_tick(int *d_t, int set, int add) { *d_t = (set >= 0 ? set : *d_t) + add; }
+__global__ void k_tick(int *d_t, int set, int add) {
+  pdl_trigger();
+  pdl_wait();
+  *d_t = (set >= 0 ? set : *d_t) + add;
+}
 
 // Reference 3D behaviour (include/fw25.h, dcmap_full3d): entries whose flat index in the WHOLE dense grid
 // ((x*nY + y)*nZ + z) is >= limit (= nX*nY) read 0.  Runs once at setup on the engine's padded copy.
@@ -97,26 +122,28 @@ void launch_inject(float *p, const long long *src_idx, const int *src_row, const
                    cudaStream_t st, const int *d_t) {
   const int n = n_src + n_air;
   if (n > 0)
-    k_inject<<<(n + 255) / 256, 256, 0, st>>>(p, src_idx, src_row, src_flag, n_src, icmat, nTic, t, d_t, air_idx, n_air);
+    launch_pdl(k_inject, dim3((n + 255) / 256), dim3(256), 0, st, p, src_idx, src_row, src_flag, n_src, icmat, nTic, t, d_t,
+               air_idx, n_air);
 }
 
 void launch_record(const float *p, const long long *sens_idx, int n_sens, float *frame, cudaStream_t st) {
-  if (n_sens > 0) k_record<<<(n_sens + 255) / 256, 256, 0, st>>>(p, sens_idx, n_sens, frame);
+  if (n_sens > 0) launch_pdl(k_record, dim3((n_sens + 255) / 256), dim3(256), 0, st, p, sens_idx, n_sens, frame);
 }
 
 void launch_record_dev(const float *p, const long long *sens_idx, int n_sens, float *frames, const int *d_t, int t_off,
                        int modT, int cap, cudaStream_t st) {
   if (n_sens > 0)
-    k_record_dev<<<(n_sens + 255) / 256, 256, 0, st>>>(p, sens_idx, n_sens, frames, d_t, t_off, modT, cap);
+    launch_pdl(k_record_dev, dim3((n_sens + 255) / 256), dim3(256), 0, st, p, sens_idx, n_sens, frames, d_t, t_off, modT,
+               cap);
 }
 
 void launch_record_box(const float *p, float *frames, long long n_sens, const int *d_t, int t_off, int modT, int cap,
                        const SensBox &B, cudaStream_t st) {
   if (n_sens <= 0) return;
   dim3 grid((B.wc + 255) / 256, B.wb, B.wa);
-  k_record_box<<<grid, 256, 0, st>>>(p, frames, n_sens, d_t, t_off, modT, cap, B);
+  launch_pdl(k_record_box, grid, dim3(256), 0, st, p, frames, n_sens, d_t, t_off, modT, cap, B);
 }
 
-void launch_tick(int *d_t, int set, int add, cudaStream_t st) { k_tick<<<1, 1, 0, st>>>(d_t, set, add); }
+void launch_tick(int *d_t, int set, int add, cudaStream_t st) { launch_pdl(k_tick, dim3(1), dim3(1), 0, st, d_t, set, add); }
 
 }  // namespace fw25

@@ -48,14 +48,22 @@ struct PwU {   // point-wise operands of one cell of fd_u
   int ci;
 };
 
-__device__ __forceinline__ PwU load_pw_u(const Fields &F, long long i) {
-  PwU w;
+// read-only maps (never written during a run: safe before pdl_wait) ...
+__device__ __forceinline__ void load_maps_u(PwU &w, const Fields &F, long long i) {
   w.ci = __ldg(F.dcmap + i);
   w.rho = __ldg(F.rho + i); w.K = __ldg(F.K + i); w.kx = __ldg(F.kappax + i);
   w.a1 = __ldg(F.ax1 + i); w.b1 = __ldg(F.bx1 + i); w.a2 = __ldg(F.ax2 + i); w.b2 = __ldg(F.bx2 + i);
+}
+// ... and the state the previous sweeps wrote
+__device__ __forceinline__ void load_state_u(PwU &w, const Fields &F, long long i) {
   w.mA1 = __ldcs(F.psi[0][0] + i); w.mA2 = __ldcs(F.psi[0][1] + i);
   w.mC1 = __ldcs(F.psi[2][0] + i); w.mC2 = __ldcs(F.psi[2][1] + i);
   w.qA = __ldcs(F.q[0] + i); w.qC = __ldcs(F.q[2] + i);
+}
+__device__ __forceinline__ PwU load_pw_u(const Fields &F, long long i) {
+  PwU w;
+  load_maps_u(w, F, i);
+  load_state_u(w, F, i);
   return w;
 }
 
@@ -64,14 +72,20 @@ struct PwP {   // point-wise operands of one cell of fd_p
   int ci;
 };
 
-__device__ __forceinline__ PwP load_pw_p(const Fields &F, long long i) {
-  PwP w;
+__device__ __forceinline__ void load_maps_p(PwP &w, const Fields &F, long long i) {
   w.ci = __ldg(F.dcmap + i);
   w.K = __ldg(F.K + i); w.beta = __ldg(F.beta + i); w.ku = __ldg(F.kappau + i);
   w.a1 = __ldg(F.au1 + i); w.b1 = __ldg(F.bu1 + i); w.a2 = __ldg(F.au2 + i); w.b2 = __ldg(F.bu2 + i);
+}
+__device__ __forceinline__ void load_state_p(PwP &w, const Fields &F, long long i) {
   w.fA1 = __ldcs(F.phi[0][0] + i); w.fA2 = __ldcs(F.phi[0][1] + i);
   w.fC1 = __ldcs(F.phi[2][0] + i); w.fC2 = __ldcs(F.phi[2][1] + i);
   w.p = F.p[i];
+}
+__device__ __forceinline__ PwP load_pw_p(const Fields &F, long long i) {
+  PwP w;
+  load_maps_p(w, F, i);
+  load_state_p(w, F, i);
   return w;
 }
 
@@ -249,22 +263,30 @@ __global__ void __launch_bounds__(TC2 * TR)
   const int tc = threadIdx.x, tr = threadIdx.y;
   const int c0 = blockIdx.x * TC2;
   const int a0 = a_lo + blockIdx.y * TR;
+  pdl_trigger();                                 // the next kernel may be scheduled once every CTA is here
   if (tc == 0 && tr == 0) {
     mbar_init(&bar, 1);
     mbar_fence_init();
-    mbar_arrive_expect_tx(&bar, HR * HC * 4);
-    tma_load_2d(&tile[0][0], &map_p, c0 - 8, a0 - 7, &bar);
   }
   __syncthreads();
   const int c = c0 + tc, a = a0 + tr;
   const bool act = c >= M && c < G.nC - M && a < a_hi;
   const long long i = (long long)a * G.sA + c;
   PwU w{};
-  if (act) w = load_pw_u(F, i);
+  StencilTab2 T{};
+  if (act) {                                     // coefficient maps and the stencil table: in flight before ...
+    load_maps_u(w, F, i);
+    T = tab[w.ci];
+  }
+  pdl_wait();                                    // ... the previous kernel (injection / fd_p: they write p) is done
+  if (tc == 0 && tr == 0) {
+    mbar_arrive_expect_tx(&bar, HR * HC * 4);
+    tma_load_2d(&tile[0][0], &map_p, c0 - 8, a0 - 7, &bar);
+  }
+  if (act) load_state_u(w, F, i);
   mbar_wait(&bar, 0);
   if (!act) return;
   const int sr = tr + 7, sc = tc + 8;
-  const StencilTab2 T = tab[w.ci];
   const float D[9] = {0.f, T.d03.x, T.d03.y, T.d03.z, T.d03.w, T.d47.x, T.d47.y, T.d47.z, T.d47.w};
   const float E = T.e.x;
   float gA = 0.f, gC = 0.f;
@@ -305,23 +327,31 @@ __global__ void __launch_bounds__(TC2 * TR)
   const int tc = threadIdx.x, tr = threadIdx.y;
   const int c0 = blockIdx.x * TC2;
   const int a0 = a_lo + blockIdx.y * TR;
+  pdl_trigger();
   if (tc == 0 && tr == 0) {
     mbar_init(&bar, 1);
     mbar_fence_init();
-    mbar_arrive_expect_tx(&bar, (UR * UC + VR * VC) * 4);
-    tma_load_2d(&tu[0][0], &map_u, c0 - 4, a0 - 8, &bar);
-    tma_load_2d(&tv[0][0], &map_v, c0 - 8, a0 - 1, &bar);
   }
   __syncthreads();
   const int c = c0 + tc, a = a0 + tr;
   const bool act = c >= M && c < G.nC - M && a < a_hi;
   const long long i = (long long)a * G.sA + c;
   PwP w{};
-  if (act) w = load_pw_p(F, i);
+  StencilTab2 T{};
+  if (act) {
+    load_maps_p(w, F, i);
+    T = tab[w.ci];
+  }
+  pdl_wait();                                    // fd_u (it writes u, v) is done
+  if (tc == 0 && tr == 0) {
+    mbar_arrive_expect_tx(&bar, (UR * UC + VR * VC) * 4);
+    tma_load_2d(&tu[0][0], &map_u, c0 - 4, a0 - 8, &bar);
+    tma_load_2d(&tv[0][0], &map_v, c0 - 8, a0 - 1, &bar);
+  }
+  if (act) load_state_p(w, F, i);
   mbar_wait(&bar, 0);
   if (!act) return;
   const int su = tc + 4, sv = tc + 8, ur = tr + 8, vr = tr + 1;
-  const StencilTab2 T = tab[w.ci];
   const float D[9] = {0.f, T.d03.x, T.d03.y, T.d03.z, T.d03.w, T.d47.x, T.d47.y, T.d47.z, T.d47.w};
   const float E = T.e.x;
   float hA = 0.f, hC = 0.f;
@@ -466,9 +496,9 @@ int launch_sweep_u_2d(const Plan2D *pl, const Fields &F, const Geom &G, int a_lo
   if (const int tr = pick_tr()) {
     dim3 grd((G.nC - M + TC2 - 1) / TC2, (a_hi - a_lo + tr - 1) / tr, 1), blk(TC2, tr, 1);
     const CUtensorMap &mp = pl->p[rpt_slot(tr)];
-    if (tr == 8) k_sweep_u_2dc<8><<<grd, blk, 0, st>>>(mp, F, G, pl->tab, a_lo, a_hi);
-    else if (tr == 4) k_sweep_u_2dc<4><<<grd, blk, 0, st>>>(mp, F, G, pl->tab, a_lo, a_hi);
-    else k_sweep_u_2dc<2><<<grd, blk, 0, st>>>(mp, F, G, pl->tab, a_lo, a_hi);
+    if (tr == 8) launch_pdl(k_sweep_u_2dc<8>, grd, blk, 0, st, mp, F, G, pl->tab, a_lo, a_hi);
+    else if (tr == 4) launch_pdl(k_sweep_u_2dc<4>, grd, blk, 0, st, mp, F, G, pl->tab, a_lo, a_hi);
+    else launch_pdl(k_sweep_u_2dc<2>, grd, blk, 0, st, mp, F, G, pl->tab, a_lo, a_hi);
     return 1;
   }
   const int rpt = pick_rpt(G, a_hi - a_lo);
@@ -486,9 +516,9 @@ int launch_sweep_p_2d(const Plan2D *pl, const Fields &F, const Geom &G, int a_lo
   if (const int tr = pick_tr()) {
     dim3 grd((G.nC - M + TC2 - 1) / TC2, (a_hi - a_lo + tr - 1) / tr, 1), blk(TC2, tr, 1);
     const CUtensorMap &mu = pl->u[rpt_slot(tr)], &mv = pl->v[rpt_slot(tr)];
-    if (tr == 8) k_sweep_p_2dc<8><<<grd, blk, 0, st>>>(mu, mv, F, G, pl->tab, a_lo, a_hi);
-    else if (tr == 4) k_sweep_p_2dc<4><<<grd, blk, 0, st>>>(mu, mv, F, G, pl->tab, a_lo, a_hi);
-    else k_sweep_p_2dc<2><<<grd, blk, 0, st>>>(mu, mv, F, G, pl->tab, a_lo, a_hi);
+    if (tr == 8) launch_pdl(k_sweep_p_2dc<8>, grd, blk, 0, st, mu, mv, F, G, pl->tab, a_lo, a_hi);
+    else if (tr == 4) launch_pdl(k_sweep_p_2dc<4>, grd, blk, 0, st, mu, mv, F, G, pl->tab, a_lo, a_hi);
+    else launch_pdl(k_sweep_p_2dc<2>, grd, blk, 0, st, mu, mv, F, G, pl->tab, a_lo, a_hi);
     return 1;
   }
   const int rpt = pick_rpt(G, a_hi - a_lo);
