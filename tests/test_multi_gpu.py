@@ -99,3 +99,21 @@ def test_two_gpu_run_against_reference_goldens(built_lib, case):
     np.testing.assert_array_equal(got, load_golden(case))
     g2 = load_golden(case, "_g2").astype(np.float64)
     assert np.linalg.norm(got - g2) / np.linalg.norm(g2) < 1e-2
+
+
+@pytest.mark.parametrize("name,lo,hi", [("het3d", (10, 9, 12), (40, 20, 31)), ("het2d_long", (0, 0), (120, 100))])
+def test_box_sensors_on_two_devices(built_lib, name, lo, hi):
+    """Box sensors split over two x-slabs (fw25_run with a device list): each slab records its planes of the box
+    without an index list and the frames come back in the global row-major order -- identical to one device."""
+    if _n_gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    import numpy as np
+
+    from fullwave25_b200 import engine
+    from tests.test_box_sensors import with_box
+    listed, boxed = with_box(name, lo, hi)
+    one, _ = engine.run(boxed)
+    two, stats = engine.run(boxed, device_ids=(0, 1))
+    assert stats["n_devices"] == 2 and np.abs(one).max() > 0
+    np.testing.assert_array_equal(two, one)
+    np.testing.assert_array_equal(engine.run(listed, device_ids=(0, 1))[0], one)
