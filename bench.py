@@ -253,7 +253,9 @@ def run_ours(args):
                 "bytes_per_step_per_interface_direction": 18 * nY * int(maps["pitch"]) * 4, "planes_sent_rank0": planes}
 
     # ---- end to end through the public API: pinned HOST maps -> upload -> K steps -> sensor frames on the host
-    frames_chk = gather_frames(drv, eng, 0, pb.ncoordsout, None)  # noqa: F841  (orders the streams)
+    # sensor frames of the resident run (steps 0 .. W+K-1): the end-to-end run below repeats steps 0 .. K-1 from HOST
+    # maps through another upload path, so its frames must be the same bits -- a full-size parity property
+    frames_chk = gather_frames(drv, eng, pb.n_frames, pb.ncoordsout, dist if world > 1 else None)
     e2e = None
     if not args.no_e2e:
         import psutil
@@ -286,6 +288,8 @@ def run_ours(args):
         barrier()
         t0 = time.perf_counter()
         eng2 = SlabEngine(pb_h, slab_e, dev)                # H2D of the 14 maps + coordinate lists happens here
+        eng2.eng.sync()
+        t_setup = time.perf_counter() - t0                  # allocation + upload (part of the timed region)
         drv2 = SlabDriver(slab_e, eng2, comm, pb_h.modT, streams=(main, bnd))
         for _ in range(K):
             drv2.step()
@@ -299,8 +303,12 @@ def run_ours(args):
         d2h = pb_h.n_frames * eng2.eng.n_local_sensors * 4
         e2e = {"value": gshape_e[0] * nY * nZ * K / dt / 1e9, "unit": UNIT,
                "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K, "seconds": dt,
+               "setup_seconds": t_setup, "upload_GBps": h2d / t_setup / 1e9,
                "grid_per_gpu": f"{e_nXl}x{nY}x{nZ}", "launches": eng2.eng.launches,
                "finite": bool(np.isfinite(out).all()) if out is not None else None,
+               "frames_identical_to_resident_run": (bool(np.array_equal(out, frames_chk[: out.shape[0]]))
+                                                    if out is not None and frames_chk is not None and e_nXl == nXl
+                                                    else None),
                "absmax": float(np.abs(out).max()) if out is not None and out.size else None,
                "api": "fullwave25_b200.runtime.SlabEngine(host maps) + SlabDriver.step + gather_frames"}
         eng2.close()

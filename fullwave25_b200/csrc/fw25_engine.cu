@@ -133,6 +133,7 @@ struct Engine {
     tiled_plan_destroy(plan);
     ws_plan_destroy(ws);
     plan2d_destroy(p2d);
+    if (stream) release_staging();
     for (void *p : owned) cudaFree(p);
     for (void *p : src_owned) cudaFree(p);
     if (stream) cudaStreamDestroy(stream);
@@ -165,10 +166,66 @@ struct Engine {
     if (on_device && src_pitch == G.pitch && !must_copy) return src;
     float *dst = dalloc<float>(cells);
     if (G.pitch != G.nC) FW_CUDA(cudaMemsetAsync(dst, 0, cells * sizeof(float), stream));
-    FW_CUDA(cudaMemcpy2DAsync(dst, (size_t)G.pitch * 4, src, (size_t)src_pitch * 4, (size_t)G.nC * 4, rows,
-                              on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream));
+    if (!on_device && src_pitch == G.nC && G.pitch != G.nC && rows * (size_t)G.nC * 4 >= ((size_t)32 << 20)) {
+      upload_dense_rows(dst, src, rows);
+    } else {
+      FW_CUDA(cudaMemcpy2DAsync(dst, (size_t)G.pitch * 4, src, (size_t)src_pitch * 4, (size_t)G.nC * 4, rows,
+                                on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream));
+    }
     if (!on_device) h2d_bytes += (int64_t)rows * G.nC * 4;
     return dst;
+  }
+
+  // Dense host rows into the padded layout.  A pitched host-to-device copy runs at 33 GB/s on a B200 (one DMA
+  // descriptor per 5 KB row), a dense one at 54 GB/s (tools/native/probe_h2d.cu): so the rows go up densely into one
+  // of two staging buffers and are re-pitched by a device-side 2-D copy on a second stream while the next chunk is
+  // in flight.
+  struct Staging {
+    float *buf[2] = {nullptr, nullptr};
+    cudaStream_t s2 = nullptr;
+    cudaEvent_t up[2] = {nullptr, nullptr}, placed[2] = {nullptr, nullptr};
+    size_t rows_per_chunk = 0;
+    int used = 0;
+  } stg;
+  void upload_dense_rows(float *dst, const float *src, size_t rows) {
+    const size_t row_b = (size_t)G.nC * 4;
+    if (!stg.buf[0]) {
+      size_t chunk_mb = 256;
+      if (const char *ev = getenv("FW25_STAGE_MB")) chunk_mb = std::max(1, atoi(ev));     // tests: force many chunks
+      stg.rows_per_chunk = std::max<size_t>(1, (chunk_mb << 20) / row_b);
+      for (int k = 0; k < 2; ++k) {
+        FW_CUDA(cudaMalloc((void **)&stg.buf[k], stg.rows_per_chunk * row_b));
+        FW_CUDA(cudaEventCreateWithFlags(&stg.up[k], cudaEventDisableTiming));
+        FW_CUDA(cudaEventCreateWithFlags(&stg.placed[k], cudaEventDisableTiming));
+      }
+      FW_CUDA(cudaStreamCreateWithFlags(&stg.s2, cudaStreamNonBlocking));
+    }
+    FW_CUDA(cudaEventRecord(stg.placed[0], stream));       // the memset of dst precedes the first placement
+    FW_CUDA(cudaStreamWaitEvent(stg.s2, stg.placed[0], 0));
+    for (size_t r0 = 0; r0 < rows; r0 += stg.rows_per_chunk) {
+      const size_t n = std::min(stg.rows_per_chunk, rows - r0);
+      const int b = stg.used & 1;
+      if (stg.used >= 2) FW_CUDA(cudaStreamWaitEvent(stream, stg.placed[b], 0));    // buffer b is free again
+      FW_CUDA(cudaMemcpyAsync(stg.buf[b], src + r0 * G.nC, n * row_b, cudaMemcpyHostToDevice, stream));
+      FW_CUDA(cudaEventRecord(stg.up[b], stream));
+      FW_CUDA(cudaStreamWaitEvent(stg.s2, stg.up[b], 0));
+      FW_CUDA(cudaMemcpy2DAsync(dst + r0 * G.pitch, (size_t)G.pitch * 4, stg.buf[b], row_b, row_b, n,
+                                cudaMemcpyDeviceToDevice, stg.s2));
+      FW_CUDA(cudaEventRecord(stg.placed[b], stg.s2));
+      ++stg.used;
+    }
+    for (int b = 0; b < 2; ++b) FW_CUDA(cudaStreamWaitEvent(stream, stg.placed[b], 0));
+  }
+  void release_staging() {
+    if (!stg.buf[0]) return;
+    cudaStreamSynchronize(stream);
+    cudaStreamSynchronize(stg.s2);
+    for (int k = 0; k < 2; ++k) {
+      cudaFree(stg.buf[k]); cudaEventDestroy(stg.up[k]); cudaEventDestroy(stg.placed[k]);
+      stg.buf[k] = nullptr;
+    }
+    cudaStreamDestroy(stg.s2);
+    stg = Staging{};
   }
 
   template <class T>
@@ -460,6 +517,7 @@ struct Engine {
       d_frames = dalloc<float>((size_t)frames_cap * std::max(n_sens, 1));
     }
     d_t = dalloc<int>(1);
+    release_staging();
     if (const char *g = getenv("FW25_GRAPH")) graph_mode = atoi(g) != 0;
     if (const char *v = getenv("FW25_VARIANT")) {   // tuning / cross-checks: force a sweep implementation
       const int want = atoi(v);

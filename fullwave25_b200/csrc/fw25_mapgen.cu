@@ -208,14 +208,13 @@ struct fw25_mapset {
   int ndim = 3, nX = 0, nY = 0, nZ = 1, pitch = 0;
   int dcmap_full3d = 1;
   size_t cells = 0;
+  float *block = nullptr;    // one allocation: the 13 maps, then dcmap
   float *maps[13] = {};
   int32_t *dcmap = nullptr;
   long long invalid = 0;
   ~fw25_mapset() {
     cudaSetDevice(device);
-    for (float *m : maps)
-      if (m) cudaFree(m);
-    if (dcmap) cudaFree(dcmap);
+    if (block) cudaFree(block);
   }
 };
 
@@ -228,7 +227,8 @@ int fw25_mapgen(const fw25_medium *md, int32_t device, fw25_mapset **out, double
   if (!md || !out) { g_err = "fw25_mapgen: NULL argument"; return 1; }
   *out = nullptr;
   std::unique_ptr<fw25_mapset> ms(new fw25_mapset());
-  std::vector<void *> tmp;   // device scratch: user-grid inputs, tables
+  void *scratch = nullptr;   // device scratch: user-grid inputs, tables
+  cudaStream_t st = nullptr;
   cudaEvent_t ev[3] = {};
   int rc = 0;
   try {
@@ -274,54 +274,59 @@ int fw25_mapgen(const fw25_medium *md, int32_t device, fw25_mapset **out, double
     P.lut_na = md->lut_na; P.lut_np = md->lut_np;
     P.alpha_min = md->alpha_min; P.alpha_max = md->alpha_max; P.power_min = md->power_min; P.power_max = md->power_max;
 
-    cudaStream_t st = nullptr;   // setup path: the legacy default stream orders uploads, kernel and frees
+    // One scratch allocation (user-grid inputs, tables) and one output allocation: a handful of driver calls
+    // whatever the number of maps.
+    MG_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     for (auto &e : ev) MG_CUDA(cudaEventCreate(&e));
-    MG_CUDA(cudaEventRecord(ev[0], st));
     const size_t upts = (size_t)md->nx * md->ny * nz_u;
-    auto up = [&](const void *host, size_t bytes) -> void * {
-      void *d = nullptr;
-      MG_CUDA(cudaMalloc(&d, bytes ? bytes : 8));
-      tmp.push_back(d);
-      if (bytes) MG_CUDA(cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, st));
-      return d;
-    };
-    P.c = (const double *)up(md->sound_speed, upts * 8);
-    P.rho = (const double *)up(md->density, upts * 8);
-    P.beta = (const double *)up(md->beta, upts * 8);
+    struct Item { const void *host; size_t bytes; const void **slot; };
+    std::vector<Item> items;
+    auto want = [&](const void *host, size_t bytes, const void **slot) { items.push_back({host, bytes, slot}); };
+    want(md->sound_speed, upts * 8, (const void **)&P.c);
+    want(md->density, upts * 8, (const void **)&P.rho);
+    want(md->beta, upts * 8, (const void **)&P.beta);
     if (direct) {
-      for (int i = 0; i < 10; ++i) P.relax[i] = (const double *)up(md->relax[i], upts * 8);
+      for (int i = 0; i < 10; ++i) want(md->relax[i], upts * 8, (const void **)&P.relax[i]);
     } else {
-      P.alpha_coeff = (const double *)up(md->alpha_coeff, upts * 8);
-      P.alpha_power = (const double *)up(md->alpha_power, upts * 8);
-      P.lut = (const double *)up(md->lut, (size_t)md->lut_na * md->lut_np * 10 * 8);
-      P.lut_alpha = (const double *)up(md->lut_alpha, (size_t)md->lut_na * 8);
-      P.lut_power = (const double *)up(md->lut_power, (size_t)md->lut_np * 8);
-      if (md->lut_invalid) P.lut_invalid = (const unsigned char *)up(md->lut_invalid, (size_t)md->lut_na * md->lut_np);
+      want(md->alpha_coeff, upts * 8, (const void **)&P.alpha_coeff);
+      want(md->alpha_power, upts * 8, (const void **)&P.alpha_power);
+      want(md->lut, (size_t)md->lut_na * md->lut_np * 10 * 8, (const void **)&P.lut);
+      want(md->lut_alpha, (size_t)md->lut_na * 8, (const void **)&P.lut_alpha);
+      want(md->lut_power, (size_t)md->lut_np * 8, (const void **)&P.lut_power);
+      if (md->lut_invalid) want(md->lut_invalid, (size_t)md->lut_na * md->lut_np, (const void **)&P.lut_invalid);
     }
+    std::vector<double> w[3];                       // per-axis weight tables, alive until the copies are done
     if (P.use_pml) {
       const int len[3] = {P.nA, P.nB, P.nC};
       const double **slot[3] = {&P.wA, &P.wB, &P.wC};
       for (int ax = 0; ax < 3; ++ax) {
         if (ndim == 2 && ax == 1) continue;
-        std::vector<double> w((size_t)3 * len[ax]);
-        fill_weights(w.data(), len[ax], m, npml + ntr, 0, md->tf_polynomial);
-        fill_weights(w.data() + len[ax], len[ax], m, npml + ntr, 0, md->tf_linear);
-        fill_weights(w.data() + 2 * (size_t)len[ax], len[ax], m, ntr, npml, md->tf_cosine);
-        *slot[ax] = (const double *)up(w.data(), w.size() * 8);
-        MG_CUDA(cudaStreamSynchronize(st));   // w goes out of scope
+        w[ax].resize((size_t)3 * len[ax]);
+        fill_weights(w[ax].data(), len[ax], m, npml + ntr, 0, md->tf_polynomial);
+        fill_weights(w[ax].data() + len[ax], len[ax], m, npml + ntr, 0, md->tf_linear);
+        fill_weights(w[ax].data() + 2 * (size_t)len[ax], len[ax], m, ntr, npml, md->tf_cosine);
+        want(w[ax].data(), w[ax].size() * 8, (const void **)slot[ax]);
       }
     }
-    unsigned long long *d_inv = (unsigned long long *)up(nullptr, 0);
-    MG_CUDA(cudaMemsetAsync(d_inv, 0, 8, st));
-    P.invalid_count = d_inv;
-
+    const unsigned long long zero = 0;
+    want(&zero, 8, (const void **)&P.invalid_count);
+    size_t total = 0;
+    for (auto &it : items) total += (it.bytes + 255) / 256 * 256;
+    MG_CUDA(cudaMalloc(&scratch, total));
     ms->cells = (size_t)P.nA * P.nB * P.pitch;
-    for (int i = 0; i < 13; ++i) {
-      MG_CUDA(cudaMalloc((void **)&ms->maps[i], ms->cells * 4));
-      P.out[i] = ms->maps[i];
+    MG_CUDA(cudaMalloc((void **)&ms->block, ms->cells * 4 * 14));
+    for (int i = 0; i < 13; ++i) P.out[i] = ms->maps[i] = ms->block + (size_t)i * ms->cells;
+    P.dcmap = ms->dcmap = reinterpret_cast<int32_t *>(ms->block + (size_t)13 * ms->cells);
+
+    MG_CUDA(cudaEventRecord(ev[0], st));
+    size_t off = 0;
+    for (auto &it : items) {
+      char *d = static_cast<char *>(scratch) + off;
+      MG_CUDA(cudaMemcpyAsync(d, it.host, it.bytes, cudaMemcpyHostToDevice, st));
+      *it.slot = d;
+      off += (it.bytes + 255) / 256 * 256;
     }
-    MG_CUDA(cudaMalloc((void **)&ms->dcmap, ms->cells * 4));
-    P.dcmap = ms->dcmap;
+    unsigned long long *d_inv = P.invalid_count;
 
     if (P.nB > 65535 || P.nA > 65535) mg_fail("fw25_mapgen: more than 65535 rows per axis");
     MG_CUDA(cudaEventRecord(ev[1], st));
@@ -342,7 +347,8 @@ int fw25_mapgen(const fw25_medium *md, int32_t device, fw25_mapset **out, double
   } catch (const MgFail &f) {
     rc = f.code;
   }
-  for (void *d : tmp) cudaFree(d);
+  if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+  if (scratch) cudaFree(scratch);
   for (auto &e : ev)
     if (e) cudaEventDestroy(e);
   if (rc) return rc;

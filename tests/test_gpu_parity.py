@@ -217,3 +217,16 @@ def test_anisotropic_file_set(built_lib, name, tmp_path):
     got_same, st = engine.run(same.normalise())
     np.testing.assert_array_equal(got_same, engine.run(iso)[0])
     np.testing.assert_array_equal(got_same, oracle.run(same))
+
+
+def test_large_host_maps_take_the_staged_upload(built_lib, monkeypatch):
+    """Host maps of >= 32 MB whose rows are not a multiple of 32 floats go up densely into two staging buffers and are
+    re-pitched on the device (Engine::upload_dense_rows); with 8 MB chunks every map needs five of them."""
+    from fullwave25_b200 import synthetic
+    monkeypatch.setenv("FW25_STAGE_MB", "8")
+    pb = synthetic.make_problem((216, 200, 203), nT=6, modT=2, seed=41, n_pml=12, n_trans=8, n_sensors=200)
+    assert pb.rho.nbytes >= 32 << 20 and pb.nZ % 32
+    want = oracle.run(pb)
+    got, stats = engine.run(pb)
+    np.testing.assert_array_equal(got, want)
+    assert np.abs(want).max() > 0 and stats["h2d_bytes"] >= 14 * pb.rho.nbytes
