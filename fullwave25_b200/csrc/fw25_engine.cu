@@ -96,6 +96,13 @@ struct Engine {
   long long *d_sens_idx = nullptr;
   int n_sens = 0, n_sens_global = 0;
   std::vector<int32_t> sens_ids;             // global outc row of each local sensor (box sensors: filled on demand)
+  // fused 2D step (k_sweep_p_2dc<2, true>): host copies of the point lists and the per-tile CSR built from them
+  std::vector<long long> h_src_idx, h_air_idx, h_sens_idx;
+  std::vector<int> h_src_row;
+  std::vector<unsigned char> h_src_flag;
+  bool fuse_ok = false;
+  Fuse2D fuse{};
+  std::vector<void *> fuse_owned;
   bool sens_box = false;                     // the sensors are every point of a box: no index list (fw25.h, out_box)
   SensBox box{};
   int sens_first = 0;                        // box sensors: global outc row of local sensor 0 (rows are contiguous)
@@ -119,7 +126,7 @@ struct Engine {
   struct StepGraph {
     cudaGraphExec_t exec = nullptr;
     int steps = 0, nodes = 0, frames = 0;
-    bool with_inject = false, records = false;
+    bool with_inject = false, records = false, fused = false;
     int variant = -1;
   } sg;
   int graph_mode = -1;           // -1: auto (on for grids <= 2^27 cells), 0: off, 1: on
@@ -134,15 +141,19 @@ struct Engine {
     ws_plan_destroy(ws);
     plan2d_destroy(p2d);
     if (stream) release_staging();
+    for (void *p : fuse_owned) cudaFree(p);
     for (void *p : owned) cudaFree(p);
     for (void *p : src_owned) cudaFree(p);
     if (stream) cudaStreamDestroy(stream);
   }
 
+  double malloc_ms = 0;        // host time spent inside cudaMalloc (FW25_SETUP_TRACE=1 prints the setup phases)
   template <class T>
   T *dalloc(size_t n) {
     void *p = nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
     FW_CUDA(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+    malloc_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     owned.push_back(p);
     return static_cast<T *>(p);
   }
@@ -190,7 +201,7 @@ struct Engine {
   void upload_dense_rows(float *dst, const float *src, size_t rows) {
     const size_t row_b = (size_t)G.nC * 4;
     if (!stg.buf[0]) {
-      size_t chunk_mb = 256;
+      size_t chunk_mb = 128;
       if (const char *ev = getenv("FW25_STAGE_MB")) chunk_mb = std::max(1, atoi(ev));     // tests: force many chunks
       stg.rows_per_chunk = std::max<size_t>(1, (chunk_mb << 20) / row_b);
       for (int k = 0; k < 2; ++k) {
@@ -265,6 +276,7 @@ struct Engine {
       n_src_rim += (r && !dead);
     }
     n_src = (int)idx.size();
+    if (ndim == 2) { h_src_idx = idx; h_src_row = row; h_src_flag = flag; }
     d_src_idx = salloc<long long>(n_src); d_src_row = salloc<int>(n_src); d_src_rim = salloc<unsigned char>(n_src);
     d_icmat = nullptr;
     if (n_src) {
@@ -286,6 +298,7 @@ struct Engine {
     FW_CUDA(cudaStreamSynchronize(stream));
     nT = nT_; nTic = nTic_;
     setup_sources(ncoords, icc, icmat);
+    build_fuse_lists();
     float *st[16] = {F.p, F.q[0], F.q[1], F.q[2], F.psi[0][0], F.psi[0][1], F.psi[1][0], F.psi[1][1], F.psi[2][0],
                      F.psi[2][1], F.phi[0][0], F.phi[0][1], F.phi[1][0], F.phi[1][1], F.phi[2][0], F.phi[2][1]};
     for (float *a : st)
@@ -297,6 +310,7 @@ struct Engine {
   }
 
   void init(const fw25_problem &pb, const fw25_slab *slab, int dev) {
+    const auto tr0 = std::chrono::steady_clock::now();
     device = dev;
     FW_CUDA(cudaSetDevice(device));
     if (pb.ndim != 2 && pb.ndim != 3) fail(1, "ndim must be 2 or 3");
@@ -408,6 +422,15 @@ struct Engine {
       FW_CUDA(cudaMemcpyAsync(d, pb.dmap, (size_t)18 * pb.ndmap * 4, cudaMemcpyDefault, stream));
       F.dmap = d;
     }
+    const bool trace = getenv("FW25_SETUP_TRACE") != nullptr;
+    auto trace_point = [&](const char *what) {
+      if (!trace) return;
+      cudaStreamSynchronize(stream);
+      fprintf(stderr, "[fw25 setup] %-28s t = %8.1f ms   (cudaMalloc so far %.1f ms, h2d %.2f GB)\n", what,
+              std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tr0).count() , malloc_ms,
+              h2d_bytes / 1e9);
+    };
+    trace_point("maps uploaded");
     // state
     auto state = [&](float *ext) {
       float *d = ext ? ext : dalloc<float>(cells);
@@ -459,6 +482,7 @@ struct Engine {
         idx.push_back(lin(c[0], c[1], nd == 3 ? c[2] : 0));
       }
       n_air = (int)idx.size();
+      if (ndim == 2) h_air_idx = idx;
       d_air_idx = dalloc<long long>(n_air);
       if (n_air) FW_CUDA(cudaMemcpyAsync(d_air_idx, idx.data(), n_air * sizeof(long long), cudaMemcpyHostToDevice, stream));
       FW_CUDA(cudaStreamSynchronize(stream));
@@ -502,6 +526,7 @@ struct Engine {
         idx.push_back(is_rim(c[0], c[1], nd == 3 ? c[2] : M) ? -1 : lin(c[0], c[1], nd == 3 ? c[2] : 0));
       }
       n_sens = (int)idx.size();
+      if (ndim == 2) h_sens_idx = idx;
       d_sens_idx = dalloc<long long>(n_sens);
       if (n_sens) FW_CUDA(cudaMemcpyAsync(d_sens_idx, idx.data(), n_sens * sizeof(long long), cudaMemcpyHostToDevice, stream));
       FW_CUDA(cudaStreamSynchronize(stream));
@@ -515,15 +540,82 @@ struct Engine {
       const size_t per = std::max<size_t>((size_t)n_sens * 4, 4);
       frames_cap = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(n_frames, 1), budget / per));
       d_frames = dalloc<float>((size_t)frames_cap * std::max(n_sens, 1));
+      // rim sensors read 0: the fused 2D step never writes their columns, so the ring starts out zeroed
+      FW_CUDA(cudaMemsetAsync(d_frames, 0, (size_t)frames_cap * std::max(n_sens, 1) * sizeof(float), stream));
     }
     d_t = dalloc<int>(1);
-    release_staging();
+    build_fuse_lists();
+    trace_point("state, plans, lists");
+    // The two staging buffers stay until the engine is destroyed: cudaFree synchronises the device and was measured
+    // at ~145 ms per buffer next to 40 GB of live allocations -- more than uploading 5 GB of maps.
     if (const char *g = getenv("FW25_GRAPH")) graph_mode = atoi(g) != 0;
     if (const char *v = getenv("FW25_VARIANT")) {   // tuning / cross-checks: force a sweep implementation
       const int want = atoi(v);
       if (want == 1 || (want == 2 && (plan || p2d)) || (want == 3 && ws)) variant = want;
     }
     FW_CUDA(cudaStreamSynchronize(stream));
+  }
+
+  // Per-tile lists of the special cells of the fused 2D step (fw25_internal.h, Fuse2D).  Whole-grid 2D engines
+  // only; a source inside the never-updated rim keeps the separate injection kernel.  Opt-in (FW25_FUSE2D=1):
+  // measured on a B200 the fused step launches 2.1 kernels per step instead of 3.2-3.6 but is no faster (14.9 vs
+  // 14.9 us at 628 x 628, 98.2 vs 96.4 us at 1457 x 2178) -- with programmatic dependent launch the two point kernels
+  // already hide behind the sweeps (profiles/README.md).
+  void build_fuse_lists() {
+    for (void *p : fuse_owned) cudaFree(p);
+    fuse_owned.clear();
+    fuse_ok = false;
+    const char *ev = getenv("FW25_FUSE2D");
+    if (!ev || atoi(ev) == 0) return;
+    if (ndim != 2 || !p2d || own_lo != 0 || own_hi != nX_global || n_src_rim > 0 || !sweeps2d_fusable()) return;
+    const int a_lo = G.a_rim_lo, a_hi = G.a_rim_hi;
+    if (a_hi <= a_lo) return;
+    const int n_bx = (G.nC - M + 127) / 128, n_by = (a_hi - a_lo + FUSE_TR - 1) / FUSE_TR;
+    const int n_tiles = n_bx * n_by;
+    struct Ent { int tile; unsigned short cell; unsigned char kind; int row; };
+    std::vector<Ent> ents;
+    auto add = [&](long long li, int kind, int row) {
+      const int a = (int)(li / G.sA), c = (int)(li % G.sA);
+      if (a < a_lo || a >= a_hi || c < M || c >= G.nC - M) return;       // rim cells are never updated
+      ents.push_back({((a - a_lo) / FUSE_TR) * n_bx + c / 128,
+                      (unsigned short)(((a - a_lo) % FUSE_TR) * 128 + c % 128), (unsigned char)kind, row});
+    };
+    for (size_t i = 0; i < h_src_idx.size(); ++i)
+      if (!(h_src_flag[i] & 2)) add(h_src_idx[i], FUSE_SOURCE, h_src_row[i]);   // (also an air voxel: zeroing wins)
+    for (long long li : h_air_idx) add(li, FUSE_AIR, 0);
+    if (!sens_box)
+      for (size_t i = 0; i < h_sens_idx.size(); ++i)
+        if (h_sens_idx[i] >= 0) add(h_sens_idx[i], FUSE_SENSOR, (int)i);
+    std::vector<int> ofs(n_tiles + 1, 0);
+    for (const Ent &e : ents) ++ofs[e.tile + 1];
+    for (int k = 0; k < n_tiles; ++k) ofs[k + 1] += ofs[k];
+    std::vector<int> pos(ofs.begin(), ofs.end() - 1), row(ents.size());
+    std::vector<unsigned short> cell(ents.size());
+    std::vector<unsigned char> kind(ents.size());
+    for (const Ent &e : ents) {                                            // stable: list order within a tile
+      const int k = pos[e.tile]++;
+      cell[k] = e.cell; kind[k] = e.kind; row[k] = e.row;
+    }
+    auto up = [&](const void *h, size_t bytes) {
+      void *d = nullptr;
+      FW_CUDA(cudaMalloc(&d, std::max<size_t>(bytes, 8)));
+      fuse_owned.push_back(d);
+      if (bytes) FW_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, stream));
+      return d;
+    };
+    fuse.tile_ofs = (const int *)up(ofs.data(), ofs.size() * sizeof(int));
+    fuse.ent_cell = (const unsigned short *)up(cell.data(), cell.size() * sizeof(unsigned short));
+    fuse.ent_kind = (const unsigned char *)up(kind.data(), kind.size());
+    fuse.ent_row = (const int *)up(row.data(), row.size() * sizeof(int));
+    FW_CUDA(cudaStreamSynchronize(stream));                                // host vectors go out of scope
+    fuse.icmat = d_icmat; fuse.nTic = nTic;
+    fuse.frames = d_frames; fuse.n_sens = n_sens; fuse.modT = modT; fuse.cap = frames_cap;
+    fuse.d_t = d_t;
+    fuse.box = box; fuse.use_box = sens_box ? 1 : 0;
+    fuse_ok = true;
+  }
+  bool use_fused_2d() const {
+    return fuse_ok && use_2d(G.a_rim_hi - G.a_rim_lo) && !use_ws() && !use_tiled();
   }
 
   bool use_ws() const { return ws != nullptr && (variant == 0 || variant == 3); }
@@ -603,16 +695,29 @@ struct Engine {
     sg.frames = 0;
     const int64_t l0 = launches;
     FW_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+    // 2D: fd_p(t) records frame t and applies the injection of step t + 1 itself (two kernels per step); only the
+    // first step of the graph is injected by k_inject and the last fd_p does not inject, so the state between graph
+    // launches is the same as after launched steps.
+    const bool fused = use_fused_2d();
+    sg.fused = fused;
     for (int j = 0; j < sg.steps; ++j) {
-      launch_inject(F.p, d_src_idx, d_src_row, d_src_rim, with_inject ? n_src : 0, d_icmat, nTic, j, d_air_idx, n_air,
-                    stream, d_t);
-      launches += ((with_inject && n_src > 0) || n_air > 0) ? 1 : 0;
+      if (!fused || j == 0) {
+        launch_inject(F.p, d_src_idx, d_src_row, d_src_rim, with_inject ? n_src : 0, d_icmat, nTic, j, d_air_idx,
+                      n_air, stream, d_t);
+        launches += ((with_inject && n_src > 0) || n_air > 0) ? 1 : 0;
+      }
       sweep_u(0, nX_global, stream);
-      sweep_p(0, nX_global, stream);
-      if (sg.records && j % modT == 0 && n_sens > 0) {
-        if (sens_box) launch_record_box(F.p, d_frames, n_sens, d_t, j, modT, frames_cap, box, stream);
-        else launch_record_dev(F.p, d_sens_idx, n_sens, d_frames, d_t, j, modT, frames_cap, stream);
-        ++launches;
+      const bool rec = sg.records && j % modT == 0 && n_sens > 0;
+      if (fused) {
+        launches += launch_sweep_p_2d_fused(p2d, F, G, G.a_rim_lo, G.a_rim_hi, stream, fuse, j,
+                                            (rec ? FUSE_RECORD : 0) | (j + 1 < sg.steps ? FUSE_INJECT : 0));
+      } else {
+        sweep_p(0, nX_global, stream);
+        if (rec) {
+          if (sens_box) launch_record_box(F.p, d_frames, n_sens, d_t, j, modT, frames_cap, box, stream);
+          else launch_record_dev(F.p, d_sens_idx, n_sens, d_frames, d_t, j, modT, frames_cap, stream);
+          ++launches;
+        }
       }
       if (sg.records && j % modT == 0) ++sg.frames;
     }
@@ -637,7 +742,7 @@ struct Engine {
       const bool phase_ok = records ? (t % modT == 0) : (t % modT != 0 && (t % modT) + steps <= modT);
       const int frames = records ? steps / modT : 0;
       if (phase_ok && steps <= max_steps && frames <= frame_room) {
-        if (!sg.exec || sg.with_inject != wi || sg.variant != variant) build_graph(wi);
+        if (!sg.exec || sg.with_inject != wi || sg.variant != variant || sg.fused != use_fused_2d()) build_graph(wi);
         if (d_t_host != t) { launch_tick(d_t, t, 0, stream); ++launches; }
         FW_CUDA(cudaGraphLaunch(sg.exec, stream));
         launches += sg.nodes;

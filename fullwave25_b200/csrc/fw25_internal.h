@@ -56,6 +56,38 @@ void plan2d_destroy(Plan2D *pl);
 int launch_sweep_u_2d(const Plan2D *pl, const Fields &F, const Geom &G, int a_lo, int a_hi, cudaStream_t st);
 int launch_sweep_p_2d(const Plan2D *pl, const Fields &F, const Geom &G, int a_lo, int a_hi, cudaStream_t st);
 
+// box sensors: local origin (a0, b0, c0) and extent (wa, wb, wc) of the owned part of the box in the engine's layout,
+// the local index ranges outside which a point lies in the never-updated rim (reads 0), array strides
+struct SensBox {
+  int a0, b0, c0, wa, wb, wc;
+  int a_lo, a_hi, b_lo, b_hi, c_lo, c_hi;
+  long long sA, sB;
+};
+// Fused 2D step (fw25_sweeps_2d.cu, k_sweep_p_2dc<TR, true>): fd_p(t) also records frame t and applies the injection
+// / air zeroing of step t + 1.  Tiles are FUSE_TR rows x 128 columns over the full sweep range [a_rim_lo, a_rim_hi):
+// tile = ((a - a_rim_lo) / FUSE_TR) * n_bx + c / 128 with n_bx = (nC - 8 + 127) / 128, cell = ((a - a_rim_lo) % FUSE_TR)
+// * 128 + c % 128.  tile_ofs is the CSR over tiles of the special cells (sources, air voxels, listed sensors).
+constexpr int FUSE_TR = 2;
+constexpr int FUSE_SOURCE = 0, FUSE_AIR = 1, FUSE_SENSOR = 2;     // ent_kind
+constexpr int FUSE_RECORD = 1, FUSE_INJECT = 2;                   // launch flags
+struct Fuse2D {
+  const int *tile_ofs;
+  const unsigned short *ent_cell;
+  const unsigned char *ent_kind;
+  const int *ent_row;            // icmat row (source) / local sensor row (listed sensor)
+  const float *icmat;
+  int nTic;
+  float *frames;                 // the frame ring [cap][n_sens]
+  long long n_sens;
+  int modT, cap;
+  const int *d_t;                // device-side step counter; this launch is step *d_t + t_off
+  SensBox box;                   // box sensors (use_box): rows follow from the cell's coordinates
+  int use_box;
+};
+bool sweeps2d_fusable();
+int launch_sweep_p_2d_fused(const Plan2D *pl, const Fields &F, const Geom &G, int a_lo, int a_hi, cudaStream_t st,
+                            const Fuse2D &X, int t_off, int flags);
+
 // point kernels: fw25_points.cu
 void launch_dcmap_mask(int32_t *dcmap, long long cells, int pitch, int nC, int nB, long long first_plane,
                        long long limit, cudaStream_t st);
@@ -66,13 +98,6 @@ void launch_record(const float *p, const long long *sens_idx, int n_sens, float 
 // graph-replayed forms: the step number is *d_t + t_off (device-side counter, advanced by launch_tick)
 void launch_record_dev(const float *p, const long long *sens_idx, int n_sens, float *frames, const int *d_t, int t_off,
                        int modT, int cap, cudaStream_t st);
-// box sensors: local origin (a0, b0, c0) and extent (wa, wb, wc) of the owned part of the box in the engine's layout,
-// the local index ranges outside which a point lies in the never-updated rim (reads 0), array strides
-struct SensBox {
-  int a0, b0, c0, wa, wb, wc;
-  int a_lo, a_hi, b_lo, b_hi, c_lo, c_hi;
-  long long sA, sB;
-};
 void launch_record_box(const float *p, float *frames, long long n_sens, const int *d_t, int t_off, int modT, int cap,
                        const SensBox &B, cudaStream_t st);
 void launch_tick(int *d_t, int set, int add, cudaStream_t st);   // *d_t = (set >= 0 ? set : *d_t) + add

@@ -315,10 +315,17 @@ __global__ void __launch_bounds__(TC2 * TR)
   F.q[0][i] = qA; F.q[2][i] = qC;
 }
 
-template <int TR>
+// FUSED: the epilogue also records this step's sensor frame and applies the NEXT step's source injection / air
+// zeroing (the reference's launch order is inject(t) -> fd_u -> fd_p -> record(t); with the injection of step t + 1
+// folded into fd_p(t) and record(t) taken from the freshly computed p' a graph-replayed 2D step is two kernels instead
+// of four).  Sensors: box sensors by arithmetic on the cell's own coordinates; listed sensors, sources and air voxels
+// through a per-tile CSR list built at setup (most tiles have none: two int loads per CTA).  A cell that is both
+// sensor and source is recorded from the register / shared copy of p' before the injected value lands.
+template <int TR, bool FUSED>
 __global__ void __launch_bounds__(TC2 * TR)
     k_sweep_p_2dc(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_v, const Fields F,
-                  const Geom G, const StencilTab2 *__restrict__ tab, int a_lo, int a_hi) {
+                  const Geom G, const StencilTab2 *__restrict__ tab, int a_lo, int a_hi, const Fuse2D X, int t_off,
+                  int flags) {
   constexpr int UR = TR + 15, UC = TC2 + 8;      // tu[r][j] = u[a0 - 8 + r][c0 - 4 + j]
   constexpr int VR = TR + 2, VC = TC2 + 16;      // tv[r][j] = v[a0 - 1 + r][c0 - 8 + j]
   __shared__ alignas(128) float tu[UR][UC];
@@ -338,9 +345,15 @@ __global__ void __launch_bounds__(TC2 * TR)
   const long long i = (long long)a * G.sA + c;
   PwP w{};
   StencilTab2 T{};
+  int e0 = 0, e1 = 0;
   if (act) {
     load_maps_p(w, F, i);
     T = tab[w.ci];
+  }
+  if (FUSED) {                                   // the tile's list bounds are setup data too
+    const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+    e0 = __ldg(X.tile_ofs + tile);
+    e1 = __ldg(X.tile_ofs + tile + 1);
   }
   pdl_wait();                                    // fd_u (it writes u, v) is done
   if (tc == 0 && tr == 0) {
@@ -350,34 +363,61 @@ __global__ void __launch_bounds__(TC2 * TR)
   }
   if (act) load_state_p(w, F, i);
   mbar_wait(&bar, 0);
-  if (!act) return;
-  const int su = tc + 4, sv = tc + 8, ur = tr + 8, vr = tr + 1;
-  const float D[9] = {0.f, T.d03.x, T.d03.y, T.d03.z, T.d03.w, T.d47.x, T.d47.y, T.d47.z, T.d47.w};
-  const float E = T.e.x;
-  float hA = 0.f, hC = 0.f;
+  float pn = 0.f;
+  if (act) {
+    const int su = tc + 4, sv = tc + 8, ur = tr + 8, vr = tr + 1;
+    const float D[9] = {0.f, T.d03.x, T.d03.y, T.d03.z, T.d03.w, T.d47.x, T.d47.y, T.d47.z, T.d47.w};
+    const float E = T.e.x;
+    float hA = 0.f, hC = 0.f;
 #pragma unroll
-  for (int k = 1; k <= M; ++k) {
-    hA = fma_(D[k], sub_(tu[ur + k - 1][su], tu[ur - k][su]), hA);
-    hC = fma_(D[k], sub_(tv[vr][sv + k - 1], tv[vr][sv - k]), hC);
+    for (int k = 1; k <= M; ++k) {
+      hA = fma_(D[k], sub_(tu[ur + k - 1][su], tu[ur - k][su]), hA);
+      hC = fma_(D[k], sub_(tv[vr][sv + k - 1], tv[vr][sv - k]), hC);
+    }
+    float cA = sub_(tu[ur][su + 1], tu[ur - 1][su + 1]);
+    cA = add_(cA, tu[ur][su - 1]); cA = sub_(cA, tu[ur - 1][su - 1]);
+    float cC = sub_(tv[vr + 1][sv], tv[vr + 1][sv - 1]);
+    cC = add_(cC, tv[vr - 1][sv]); cC = sub_(cC, tv[vr - 1][sv - 1]);
+    const float dX = G.dX;
+    hA = div_(fma_(E, cA, hA), dX);
+    hC = div_(fma_(E, cC, hC), dX);
+    const float fA1 = fma_(w.b1, w.fA1, mul_(hA, w.a1));
+    const float fA2 = fma_(w.b2, w.fA2, mul_(hA, w.a2));
+    const float fC1 = fma_(w.b1, w.fC1, mul_(hC, w.a1));
+    const float fC2 = fma_(w.b2, w.fC2, mul_(hC, w.a2));
+    float S = add_(div_(hA, w.ku), div_(hC, w.ku));
+    S = add_(fA1, S); S = add_(fA2, S); S = add_(fC1, S); S = add_(fC2, S);
+    const float At = mul_(mul_(G.dT, w.K), S);
+    const float Bt = fma_(w.p, mul_(rcp_(w.K), sub_(1.0f, add_(w.beta, w.beta))), 1.0f);
+    __stcs(F.phi[0][0] + i, fA1); __stcs(F.phi[0][1] + i, fA2);
+    __stcs(F.phi[2][0] + i, fC1); __stcs(F.phi[2][1] + i, fC2);
+    pn = fma_(-At, Bt, w.p);
+    F.p[i] = pn;
   }
-  float cA = sub_(tu[ur][su + 1], tu[ur - 1][su + 1]);
-  cA = add_(cA, tu[ur][su - 1]); cA = sub_(cA, tu[ur - 1][su - 1]);
-  float cC = sub_(tv[vr + 1][sv], tv[vr + 1][sv - 1]);
-  cC = add_(cC, tv[vr - 1][sv]); cC = sub_(cC, tv[vr - 1][sv - 1]);
-  const float dX = G.dX;
-  hA = div_(fma_(E, cA, hA), dX);
-  hC = div_(fma_(E, cC, hC), dX);
-  const float fA1 = fma_(w.b1, w.fA1, mul_(hA, w.a1));
-  const float fA2 = fma_(w.b2, w.fA2, mul_(hA, w.a2));
-  const float fC1 = fma_(w.b1, w.fC1, mul_(hC, w.a1));
-  const float fC2 = fma_(w.b2, w.fC2, mul_(hC, w.a2));
-  float S = add_(div_(hA, w.ku), div_(hC, w.ku));
-  S = add_(fA1, S); S = add_(fA2, S); S = add_(fC1, S); S = add_(fC2, S);
-  const float At = mul_(mul_(G.dT, w.K), S);
-  const float Bt = fma_(w.p, mul_(rcp_(w.K), sub_(1.0f, add_(w.beta, w.beta))), 1.0f);
-  __stcs(F.phi[0][0] + i, fA1); __stcs(F.phi[0][1] + i, fA2);
-  __stcs(F.phi[2][0] + i, fC1); __stcs(F.phi[2][1] + i, fC2);
-  F.p[i] = fma_(-At, Bt, w.p);
+  if (!FUSED) return;
+
+  const int t = *X.d_t + t_off;
+  float *frame = X.frames + (size_t)((t / X.modT) % X.cap) * X.n_sens;
+  if ((flags & FUSE_RECORD) && X.use_box && act) {           // box sensor: this cell's row follows from (a, c)
+    const int ba = a - X.box.a0, bc = c - X.box.c0;
+    if (ba >= 0 && ba < X.box.wa && bc >= 0 && bc < X.box.wc) frame[(size_t)ba * X.box.wc + bc] = pn;
+  }
+  if (e1 > e0) {                                             // uniform over the CTA
+    float *pnew = &tu[0][0];                                 // the u tile is dead: reuse it for the tile's p'
+    __syncthreads();
+    pnew[tr * TC2 + tc] = pn;
+    __syncthreads();                                         // p' stored (shared AND global) by every owner thread
+    for (int e = e0 + tr * TC2 + tc; e < e1; e += TR * TC2) {
+      const int kind = X.ent_kind[e], cell = X.ent_cell[e], row = X.ent_row[e];
+      if (kind == FUSE_SENSOR) {
+        if (flags & FUSE_RECORD) frame[row] = pnew[cell];
+      } else if (flags & FUSE_INJECT) {
+        const long long idx = (long long)(a0 + cell / TC2) * G.sA + c0 + cell % TC2;
+        if (kind == FUSE_AIR) F.p[idx] = 0.0f;
+        else if (t + 1 < X.nTic) F.p[idx] = X.icmat[(size_t)row * X.nTic + t + 1];
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------ host
@@ -516,9 +556,10 @@ int launch_sweep_p_2d(const Plan2D *pl, const Fields &F, const Geom &G, int a_lo
   if (const int tr = pick_tr()) {
     dim3 grd((G.nC - M + TC2 - 1) / TC2, (a_hi - a_lo + tr - 1) / tr, 1), blk(TC2, tr, 1);
     const CUtensorMap &mu = pl->u[rpt_slot(tr)], &mv = pl->v[rpt_slot(tr)];
-    if (tr == 8) launch_pdl(k_sweep_p_2dc<8>, grd, blk, 0, st, mu, mv, F, G, pl->tab, a_lo, a_hi);
-    else if (tr == 4) launch_pdl(k_sweep_p_2dc<4>, grd, blk, 0, st, mu, mv, F, G, pl->tab, a_lo, a_hi);
-    else launch_pdl(k_sweep_p_2dc<2>, grd, blk, 0, st, mu, mv, F, G, pl->tab, a_lo, a_hi);
+    const Fuse2D none{};
+    if (tr == 8) launch_pdl(k_sweep_p_2dc<8, false>, grd, blk, 0, st, mu, mv, F, G, pl->tab, a_lo, a_hi, none, 0, 0);
+    else if (tr == 4) launch_pdl(k_sweep_p_2dc<4, false>, grd, blk, 0, st, mu, mv, F, G, pl->tab, a_lo, a_hi, none, 0, 0);
+    else launch_pdl(k_sweep_p_2dc<2, false>, grd, blk, 0, st, mu, mv, F, G, pl->tab, a_lo, a_hi, none, 0, 0);
     return 1;
   }
   const int rpt = pick_rpt(G, a_hi - a_lo);
@@ -528,6 +569,18 @@ int launch_sweep_p_2d(const Plan2D *pl, const Fields &F, const Geom &G, int a_lo
   else if (rpt == 4) k_sweep_p_2d<4><<<grd, TC2, 0, st>>>(mu, mv, F, G, pl->tab, a_lo, a_hi);
   else if (rpt == 2) k_sweep_p_2d<2><<<grd, TC2, 0, st>>>(mu, mv, F, G, pl->tab, a_lo, a_hi);
   else k_sweep_p_2d<1><<<grd, TC2, 0, st>>>(mu, mv, F, G, pl->tab, a_lo, a_hi);
+  return 1;
+}
+
+// ---- fused fd_p (2D, graph-replayed whole-grid steps): see k_sweep_p_2dc<TR, FUSED>
+bool sweeps2d_fusable() { return pick_tr() == FUSE_TR; }
+
+int launch_sweep_p_2d_fused(const Plan2D *pl, const Fields &F, const Geom &G, int a_lo, int a_hi, cudaStream_t st,
+                            const Fuse2D &X, int t_off, int flags) {
+  if (a_hi <= a_lo) return 0;
+  dim3 grd((G.nC - M + TC2 - 1) / TC2, (a_hi - a_lo + FUSE_TR - 1) / FUSE_TR, 1), blk(TC2, FUSE_TR, 1);
+  const CUtensorMap &mu = pl->u[rpt_slot(FUSE_TR)], &mv = pl->v[rpt_slot(FUSE_TR)];
+  launch_pdl(k_sweep_p_2dc<FUSE_TR, true>, grd, blk, 0, st, mu, mv, F, G, pl->tab, a_lo, a_hi, X, t_off, flags);
   return 1;
 }
 

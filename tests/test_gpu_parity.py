@@ -230,3 +230,41 @@ def test_large_host_maps_take_the_staged_upload(built_lib, monkeypatch):
     got, stats = engine.run(pb)
     np.testing.assert_array_equal(got, want)
     assert np.abs(want).max() > 0 and stats["h2d_bytes"] >= 14 * pb.rho.nbytes
+
+
+@pytest.mark.parametrize("name", ["het2d", "het2d_long", "het2d_ragged", "hom2d", "far2d"])
+@pytest.mark.parametrize("sensors", ["listed", "box"])
+def test_fused_2d_step_equals_separate_kernels(built_lib, name, sensors, monkeypatch):
+    """Graph-replayed 2D steps fold record(t) and inject(t + 1) into fd_p(t) (k_sweep_p_2dc<2, true>): two kernels per
+    step instead of up to four, same bits as the separate kernels and the oracle -- including sensors that sit on
+    source cells and air voxels, rim sensors, duplicate sensors and runs that stop inside a recording period."""
+    pb = cases.make(name)
+    pb.nT -= 3
+    if sensors == "box":
+        pb.outc = np.stack(np.meshgrid(np.arange(2, pb.nX - 5), np.arange(0, pb.nY), indexing="ij"), -1).reshape(-1, 2)
+    else:
+        extra = [pb.icc[:5], pb.icc[-3:], pb.outc[:2], [[3, 40], [40, 2]]]
+        if pb.ncoordszero:
+            extra.append(pb.icczero[:4])
+            pb.icczero = np.vstack([pb.icczero, pb.icc[7:9]])          # sources that are air voxels too
+        pb.outc = np.vstack([pb.outc] + extra)
+    pb.outc = pb.outc.astype(np.int32)
+    pb.icczero = pb.icczero.astype(np.int32)
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("FW25_FUSE2D", mode)
+        out[mode] = engine.run(pb)
+    np.testing.assert_array_equal(out["1"][0], out["0"][0])
+    np.testing.assert_array_equal(out["1"][0], oracle.run(pb))
+    assert out["1"][1]["kernel_launches"] < 0.75 * out["0"][1]["kernel_launches"]
+    assert np.abs(out["1"][0]).max() > 0
+    # several transmit events on one engine: the lists follow the new sources
+    with engine.Engine(pb) as e:
+        first, _ = e.run()
+        e.reset(pb.icc[::2], pb.icmat[::2] * 0.5)
+        second, _ = e.run()
+    np.testing.assert_array_equal(first, out["1"][0])
+    half = cases.make(name)
+    half.nT, half.outc, half.icczero = pb.nT, pb.outc, pb.icczero
+    half.icc, half.icmat = pb.icc[::2], pb.icmat[::2] * np.float32(0.5)
+    np.testing.assert_array_equal(second, oracle.run(half))
