@@ -102,6 +102,7 @@ class _LiveEngine:
 def release() -> None:
     """Free the engine (and its device-resident maps) kept alive for static-map reuse."""
     _LiveEngine.release()
+    _StaticSession.release()
 
 
 def _run_dat_dir(simulation_dir: Path, device_ids) -> tuple[np.ndarray, dict]:
@@ -190,18 +191,67 @@ class Launcher:
         return flat
 
 
-def install(fullwave_module=None):
-    """Make the reference's `Solver` use this launcher: replaces `fullwave.solver.solver.Launcher` (the name
-    `Solver.__init__` instantiates, solver.py:510-515) and `SimulationError`.  Returns an `uninstall` callable."""
+class _StaticSession:
+    """The live engine of a static-map transmit sequence run through the patched `Solver.run` (install(in_memory=True))."""
+    session: "Session | None" = None
+    medium_ref = None
+
+    @classmethod
+    def release(cls):
+        if cls.session is not None:
+            cls.session.close()
+        cls.session, cls.medium_ref = None, None
+
+
+def install(fullwave_module=None, *, in_memory: bool = False, maps: str = "host"):
+    """Make the reference's `Solver` use this engine.  Returns an `uninstall` callable.
+
+    Default: replaces `fullwave.solver.solver.Launcher` (the name `Solver.__init__` instantiates, solver.py:510-515):
+    `Solver.run` still writes its .dat directory and reads genout.dat back, only the launch is in-process.
+
+    in_memory=True additionally replaces `Solver.run` (solver.py:620-778) itself, same signature and return value:
+    nothing touches the disk, and with maps="device" `PMLBuilder.run` is replaced by the GPU map builder as well
+    (`run_solver`).  `is_static_map=True` keeps the engine and its maps alive between transmit events exactly like
+    upstream keeps the .dat files: `recalculate_pml=True` starts a sequence, `False` reuses it.  Calls that need the
+    directory (`load_results=False`, exponential attenuation) fall through to the original method."""
     import importlib
+    import weakref
     sol = importlib.import_module("fullwave.solver.solver")
     lau = importlib.import_module("fullwave.solver.launcher")
-    saved = (sol.Launcher, lau.Launcher)
+    saved = (sol.Launcher, lau.Launcher, sol.Solver.run)
     sol.Launcher = Launcher
     lau.Launcher = Launcher
+    if maps not in ("host", "device"):
+        raise ValueError('maps must be "host" or "device"')
+
+    if in_memory:
+        original_run = sol.Solver.run
+
+        def run(self, simulation_dir_name="txrx_0", *, is_static_map=False, recalculate_pml=True,
+                record_whole_domain=False, sampling_modulus_time_whole_domain=1, load_results=True):
+            if not load_results or getattr(self, "use_exponential_attenuation", False):
+                return original_run(self, simulation_dir_name, is_static_map=is_static_map,
+                                    recalculate_pml=recalculate_pml, record_whole_domain=record_whole_domain,
+                                    sampling_modulus_time_whole_domain=sampling_modulus_time_whole_domain,
+                                    load_results=load_results)
+            session = None
+            if is_static_map:
+                med = self.pml_builder.medium_org
+                same = (_StaticSession.session is not None and _StaticSession.medium_ref is not None
+                        and _StaticSession.medium_ref() is med)
+                if recalculate_pml or not same:
+                    _StaticSession.release()
+                    _StaticSession.session, _StaticSession.medium_ref = Session(), weakref.ref(med)
+                session = _StaticSession.session
+            return run_solver(self, record_whole_domain=record_whole_domain,
+                              sampling_modulus_time_whole_domain=sampling_modulus_time_whole_domain,
+                              maps=maps, session=session)
+
+        sol.Solver.run = run
 
     def uninstall():
-        sol.Launcher, lau.Launcher = saved
+        sol.Launcher, lau.Launcher, sol.Solver.run = saved
+        _StaticSession.release()
     return uninstall
 
 

@@ -220,3 +220,44 @@ def test_anisotropic_solver_run_identical_through_every_boundary(built_lib, shap
     assert want.shape == (12, 20) and np.abs(want).max() > 0
     for name, got in out.items():
         np.testing.assert_array_equal(got, want, err_msg=name)
+
+
+@needs_ref
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(40, 48), (20, 24, 28)])
+def test_patched_solver_run_in_memory(built_lib, shape):
+    """`launcher.install(in_memory=True)`: the user's script keeps calling `fullwave.Solver(...).run(...)` -- same
+    signature, same return value -- and nothing touches the disk.  maps="host" is bit-identical to the reference
+    binary, maps="device" within 1e-5 relative L2; a static-map transmit sequence reuses the engine; calls that need the
+    directory (load_results=False) still go through the original method."""
+    import os
+    from fullwave25_b200 import build
+    fw, grid, medium, source, sensor = ref_objects.build(shape, n_steps=60, n_sensors=12, n_air=0, modT=3)
+    kw = dict(pml_layer_thickness_px=6, n_transition_layer=4)
+    with tempfile.TemporaryDirectory() as td:
+        want = fw.Solver(Path(td) / "ref", grid, medium, source, sensor,
+                         path_fullwave_simulation_bin=ref_objects.ref_bin(len(shape)), **kw).run()
+        for maps in ("host", "device"):
+            undo = launcher.install(in_memory=True, maps=maps)
+            try:
+                s = fw.Solver(Path(td) / f"mem_{maps}", grid, medium, source, sensor,
+                              path_fullwave_simulation_bin=build.CLI, **kw)
+                got = s.run()
+                assert not (Path(td) / f"mem_{maps}" / "txrx_0").exists()          # no simulation directory
+                if maps == "host":
+                    np.testing.assert_array_equal(got, want)
+                else:
+                    assert np.linalg.norm(got.astype(np.float64) - want) <= 1e-5 * np.linalg.norm(want.astype(np.float64))
+                # a transmit sequence on a static map: event 0 builds, events 1, 2 reuse the engine
+                seq = [fw.Solver(Path(td) / f"seq_{maps}", grid, medium, source, sensor,
+                                 path_fullwave_simulation_bin=build.CLI, **kw)
+                       .run(f"txrx_{k}", is_static_map=True, recalculate_pml=(k == 0)) for k in range(3)]
+                assert launcher._StaticSession.session is not None and launcher._StaticSession.session.eng is not None
+                for ev in seq:
+                    np.testing.assert_array_equal(ev, got)
+                path = s.run("to_disk", load_results=False)                          # falls through: directory + genout.dat
+                assert os.path.exists(path) and str(path).endswith("genout.dat")
+            finally:
+                undo()
+            assert launcher._StaticSession.session is None
+            assert fw.Solver.run.__module__.startswith("fullwave")
