@@ -218,7 +218,7 @@ def install(fullwave_module=None, *, in_memory: bool = False, maps: str = "host"
     import weakref
     sol = importlib.import_module("fullwave.solver.solver")
     lau = importlib.import_module("fullwave.solver.launcher")
-    saved = (sol.Launcher, lau.Launcher, sol.Solver.run)
+    saved = (sol.Launcher, lau.Launcher, sol.Solver.run, sol.PMLBuilder)
     sol.Launcher = Launcher
     lau.Launcher = Launcher
     if maps not in ("host", "device"):
@@ -248,19 +248,87 @@ def install(fullwave_module=None, *, in_memory: bool = False, maps: str = "host"
                               maps=maps, session=session)
 
         sol.Solver.run = run
+        if maps == "device":       # `Solver.__init__` then no longer pads anything on the host (solver.py:527-536)
+            sol.PMLBuilder = lazy_pml_builder_class(sol.PMLBuilder)
 
     def uninstall():
-        sol.Launcher, lau.Launcher, sol.Solver.run = saved
+        sol.Launcher, lau.Launcher, sol.Solver.run, sol.PMLBuilder = saved
         _StaticSession.release()
     return uninstall
 
 
-def _sensor_and_box(solver, record_whole_domain: bool, modulus: int):
+def lean_lists(pmlb):
+    """(source, sensor, air coordinates) on the EXTENDED grid straight from the user-grid objects: the reference pads
+    the masks with zeros (`_extend_map_for_pml(..., fill_edge=False)`, pml_builder.py:243-262) and lists the non-zero
+    cells in row-major order (utils/coordinates.py:28-53), which is the original list shifted by the boundary width."""
+    from types import SimpleNamespace
+    nb = int(pmlb.num_boundary_points)
+    src, sen, med = pmlb.source_org, pmlb.sensor_org, pmlb.medium_org
+    source = SimpleNamespace(incoords=np.asarray(src.incoords) + nb, icmat=src.icmat)
+    sensor = SimpleNamespace(outcoords=np.asarray(sen.outcoords) + nb,
+                             sampling_modulus_time=sen.sampling_modulus_time)
+    air = np.asarray(med.air_map)
+    icczero = (np.stack(np.nonzero(air != 0), axis=1) + nb) if air.any() else np.zeros((0, air.ndim), np.int64)
+    return source, sensor, icczero
+
+
+def lazy_pml_builder_class(PMLBuilder):
+    """A `PMLBuilder` with the same constructor and attributes whose expensive part -- padding the medium, source and
+    sensor to the extended grid in `__init__` (pml_builder.py:222-262; 7 s for 120^3) -- happens only when something
+    asks for `extended_medium / extended_source / extended_sensor / pml_mask_*` or calls `run()`.  The GPU map builder
+    needs none of them (`MediumSpec.from_pml_builder` reads the user-grid medium, `lean_lists` the user-grid masks)."""
+    import fullwave
+
+    class LazyPMLBuilder(PMLBuilder):
+        def __init__(self, grid, medium, source, sensor, *, m_spatial_order=8, n_pml_layer=40, n_transition_layer=40,
+                     use_isotropic_relaxation=False):
+            self._ctor = (grid, medium, source, sensor, dict(
+                m_spatial_order=m_spatial_order, n_pml_layer=n_pml_layer, n_transition_layer=n_transition_layer,
+                use_isotropic_relaxation=use_isotropic_relaxation))
+            self._full = None
+            self.grid_org, self.medium_org, self.source_org, self.sensor_org = grid, medium, source, sensor
+            self.is_3d = grid.is_3d
+            self.use_isotropic_relaxation = use_isotropic_relaxation
+            self.m_spatial_order, self.n_pml_layer = m_spatial_order, n_pml_layer
+            self.n_transition_layer = n_transition_layer
+            nb = self.num_boundary_points
+            deltas = (grid.dx, grid.dy, grid.dz) if self.is_3d else (grid.dx, grid.dy)
+            domain_size = tuple((n + 2 * nb) * d for n, d in zip(np.asarray(medium.sound_speed).shape, deltas))
+            self.extended_grid = fullwave.Grid(domain_size=domain_size, f0=grid.f0, duration=grid.duration,
+                                               c0=grid.c0, ppw=grid.ppw, cfl=grid.cfl)
+            self.pml_layer_m = self.extended_grid.dx * n_pml_layer
+            self.transition_layer_m = self.extended_grid.dx * n_transition_layer
+            self.n_polynomial = 2
+            self.theoritical_reflection_coefficient = 10 ** (-30)
+            if self.n_pml_layer == 0:
+                self.n_transition_layer = 0
+
+        def _materialise(self):
+            if self._full is None:
+                g, m, s, r, kw = self._ctor
+                self._full = PMLBuilder(g, m, s, r, **kw)
+            return self._full
+
+        extended_medium = property(lambda self: self._materialise().extended_medium)
+        extended_source = property(lambda self: self._materialise().extended_source)
+        extended_sensor = property(lambda self: self._materialise().extended_sensor)
+        pml_mask_x = property(lambda self: self._materialise().pml_mask_x)
+        pml_mask_y = property(lambda self: self._materialise().pml_mask_y)
+        pml_mask_z = property(lambda self: self._materialise().pml_mask_z)
+
+        def run(self, *, use_pml=True):
+            return self._materialise().run(use_pml=use_pml)
+
+    LazyPMLBuilder.__name__ = "PMLBuilder"
+    return LazyPMLBuilder
+
+
+def _sensor_and_box(solver, record_whole_domain: bool, modulus: int, lean: bool = False):
     """(sensor, out_box).  `record_whole_domain` (solver.py:709-731) upstream builds a `Sensor` whose mask is the whole
     extended grid -- one coordinate row per grid point.  Here it is a box (fw25.h, out_box): no mask, no coordinate
     list on the host, no index list on the device; the frames come back in the same row-major order."""
     if not record_whole_domain:
-        return solver.pml_builder.extended_sensor, None
+        return (lean_lists(solver.pml_builder)[1] if lean else solver.pml_builder.extended_sensor), None
     from types import SimpleNamespace
     eg = solver.pml_builder.extended_grid
     shape = (int(eg.nx), int(eg.ny), int(eg.nz)) if solver.is_3d else (int(eg.nx), int(eg.ny))
@@ -280,9 +348,10 @@ def _run_solver_device_maps(solver, sensor, out_box, device: int, session: Sessi
         logger.warning("Warning: Some attenuation values correspond to invalid relaxation parameters. "
                        "This is due to the limitations of the precomputed lookup table. "
                        "Please change the attenuation values.\nNumber of invalid points: %d.", ms.invalid_count)
-    # the reference's anisotropic binaries have no inject_source_zero kernel: they ignore the air map (fw25.h)
-    air = pmlb.extended_medium.air_map if getattr(solver, "use_isotropic_relaxation", True) else None
-    pb = Problem.for_device_maps(ms, pmlb.extended_grid, pmlb.extended_source, sensor, air_map=air, out_box=out_box)
+    source, _, icczero = lean_lists(pmlb)
+    if not getattr(solver, "use_isotropic_relaxation", True):
+        icczero = icczero[:0]      # the reference's anisotropic binaries have no inject_source_zero kernel (fw25.h)
+    pb = Problem.for_device_maps(ms, pmlb.extended_grid, source, sensor, out_box=out_box, icczero=icczero)
     eng = engine.Engine(pb, device=device, device_maps=ms.device_maps())
     setup_s = time.perf_counter() - t0
     try:
@@ -310,7 +379,7 @@ def run_solver(solver, *, record_whole_domain: bool = False, sampling_modulus_ti
         raise ValueError('maps must be "host" or "device"')
     ids = device_ids_of(cuda_device_id if cuda_device_id is not None else getattr(solver, "cuda_device_id", None))
     if maps == "device" and len(ids) == 1 and not (session is not None and session.eng is not None):
-        sensor, out_box = _sensor_and_box(solver, record_whole_domain, sampling_modulus_time_whole_domain)
+        sensor, out_box = _sensor_and_box(solver, record_whole_domain, sampling_modulus_time_whole_domain, lean=True)
         try:
             genout, stats, pb = _run_solver_device_maps(solver, sensor, out_box, ids[0], session)
         except engine.EngineError as e:
@@ -318,7 +387,7 @@ def run_solver(solver, *, record_whole_domain: bool = False, sampling_modulus_ti
         result = genout.reshape(-1, pb.ncoordsout).T
         return (result, stats) if return_stats else result
     if session is not None and session.eng is not None:      # next transmit event: only the sources change
-        src = solver.pml_builder.extended_source
+        src = lean_lists(solver.pml_builder)[0]
         eg = solver.pml_builder.extended_grid
         shape = (eg.nx, eg.ny, eg.nz) if solver.is_3d else (eg.nx, eg.ny)
         if tuple(shape) != tuple(session.shape):

@@ -284,14 +284,17 @@ class Problem:
         return pb.normalise()
 
     @classmethod
-    def for_device_maps(cls, mapset, grid, source, sensor, air_map=None, out_box=None) -> "Problem":
+    def for_device_maps(cls, mapset, grid, source, sensor, air_map=None, out_box=None, icczero=None) -> "Problem":
         """Engine input whose 13 maps + dcmap already sit in HBM (`mapgen.MapSet`): only the step counts, the
         stencil table and the source / sensor / air-voxel lists come from the host.  grid, source, sensor: the
-        reference's PML-extended objects (as in `from_fullwave_objects`); air_map: the extended air map."""
+        reference's PML-extended objects (as in `from_fullwave_objects`) or anything with the same attributes;
+        air voxels: the extended air map, or their coordinates (`icczero`) directly."""
         is_3d = len(mapset.shape) == 3
         icmat = np.asarray(source.icmat)
         nd = 3 if is_3d else 2
         air = None if air_map is None else np.asarray(air_map)
+        if icczero is not None:
+            air = None
         none_maps = {name: None for name in MAP_NAMES}
         pb = cls(
             ndim=nd, nX=int(mapset.shape[0]), nY=int(mapset.shape[1]), nZ=int(mapset.shape[2]) if is_3d else 1,
@@ -300,7 +303,8 @@ class Problem:
             dmap=mapset.dmap, dcmap=None,
             icc=np.asarray(source.incoords), icmat=icmat,
             outc=np.zeros((0, nd), np.int32) if out_box is not None else np.asarray(sensor.outcoords),
-            icczero=(np.stack(np.nonzero(air != 0), axis=1) if air is not None and air.any()
+            icczero=(np.asarray(icczero) if icczero is not None else
+                     np.stack(np.nonzero(air != 0), axis=1) if air is not None and air.any()
                      else np.zeros((0, nd), np.int32)),
             extra={"d": mapset.d_table, "c0": getattr(grid, "c0", 1540.0)},
             dcmap_full3d=True,       # a reference-style truncation is already inside the generated dcmap

@@ -56,6 +56,39 @@ def test_in_memory_problem_equals_reference_dat_directory(shape):
     assert 0 < from_files.ncoordszero <= 5 and from_files.ncoordsout == 9
 
 
+@needs_ref
+@pytest.mark.parametrize("shape", [(20, 24), (12, 14, 16)])
+def test_lean_lists_and_lazy_pml_builder_equal_the_reference_objects(shape):
+    """What the in-memory device path uses instead of the padded objects: coordinate lists shifted by the boundary
+    width == the reference's extended source / sensor / air lists; the lazy PMLBuilder exposes the same grid and layer
+    attributes without padding anything, and materialises the real builder on demand."""
+    from fullwave.solver.pml_builder import PMLBuilder
+    from fullwave25_b200 import mapgen
+    fw, grid, medium, source, sensor = ref_objects.build(shape, n_steps=30, n_sensors=9, n_air=5)
+    kw = dict(m_spatial_order=8, n_pml_layer=6, n_transition_layer=4, use_isotropic_relaxation=True)
+    real = PMLBuilder(grid, medium, source, sensor, **kw)
+    lazy = launcher.lazy_pml_builder_class(PMLBuilder)(grid, medium, source, sensor, **kw)
+    src, sen, air = launcher.lean_lists(lazy)
+    np.testing.assert_array_equal(src.incoords, real.extended_source.incoords)
+    np.testing.assert_array_equal(src.icmat, real.extended_source.icmat)
+    np.testing.assert_array_equal(sen.outcoords, real.extended_sensor.outcoords)
+    assert sen.sampling_modulus_time == real.extended_sensor.sampling_modulus_time
+    np.testing.assert_array_equal(air, np.stack(np.nonzero(real.extended_medium.air_map), axis=1))
+    for a in ("nx", "ny", "nt", "num_boundary_points", "pml_layer_m", "transition_layer_m", "n_polynomial",
+              "theoritical_reflection_coefficient", "is_3d"):
+        assert getattr(lazy, a) == getattr(real, a), a
+    for a in ("dt", "dx", "c0", "cfl", "nx", "ny", "nt"):
+        assert getattr(lazy.extended_grid, a) == getattr(real.extended_grid, a), a
+    s1, s2 = mapgen.MediumSpec.from_pml_builder(lazy), mapgen.MediumSpec.from_pml_builder(real)
+    assert s1.extended_shape == s2.extended_shape and s1.d_target_pml() == s2.d_target_pml()
+    assert isinstance(lazy, PMLBuilder) and lazy._full is None            # nothing padded so far
+    ext = lazy.run(use_pml=True)                                         # the host path still works: materialised now
+    want = real.run(use_pml=True)
+    for k, v in want.relaxation_param_dict_for_fw2.items():
+        np.testing.assert_array_equal(ext.relaxation_param_dict_for_fw2[k], v, err_msg=k)
+    np.testing.assert_array_equal(lazy.extended_source.incoords, real.extended_source.incoords)
+
+
 def test_device_id_forms_match_reference_launcher():
     assert launcher.parse_cuda_device_id(None) == "0"
     assert launcher.parse_cuda_device_id(2) == "2"
@@ -244,6 +277,8 @@ def test_patched_solver_run_in_memory(built_lib, shape):
                               path_fullwave_simulation_bin=build.CLI, **kw)
                 got = s.run()
                 assert not (Path(td) / f"mem_{maps}" / "txrx_0").exists()          # no simulation directory
+                if maps == "device":                                               # ... and nothing padded on the host
+                    assert type(s.pml_builder).__name__ == "PMLBuilder" and s.pml_builder._full is None
                 if maps == "host":
                     np.testing.assert_array_equal(got, want)
                 else:

@@ -56,6 +56,21 @@ with tempfile.TemporaryDirectory(dir="/dev/shm") as td:
     got, stats = out.pop("run_solver_no_disk")
     out["run_solver_no_disk"] = got
     res["engine_stats_no_disk"] = {k: (float(v) if isinstance(v, float) else int(v)) for k, v in stats.items()}
+    # GPU-built maps (fw25_mapgen) instead of PMLBuilder.run, and the patched Solver.run a user's script would call
+    timed("run_solver_device_maps", lambda: launcher.run_solver(s_ref, maps="device", return_stats=True))
+    got, stats = out.pop("run_solver_device_maps")
+    res["rel_l2_device_maps_vs_reference"] = float(
+        np.linalg.norm(got.astype(np.float64) - out["reference_solver_run"]) /
+        np.linalg.norm(out["reference_solver_run"].astype(np.float64)))
+    res["engine_stats_device_maps"] = {k: (v if isinstance(v, str) else float(v)) for k, v in stats.items()}
+    undo = launcher.install(in_memory=True, maps="device")
+    try:
+        def user_script():
+            return fw.Solver(Path(td) / "mem", grid, medium, source, sensor, path_fullwave_simulation_bin=build.CLI).run()
+        timed("patched_solver_construct_and_run_device_maps", user_script)
+        out.pop("patched_solver_construct_and_run_device_maps")
+    finally:
+        undo()
 want = out.pop("reference_solver_run")
 for k, v in out.items():
     res[k + "_bit_identical"] = bool(np.array_equal(v, want))
