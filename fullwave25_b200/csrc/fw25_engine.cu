@@ -8,6 +8,10 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <mutex>
+#include <deque>
+#include <condition_variable>
+#include <atomic>
 #include <chrono>
 #include <climits>
 #include <cstdio>
@@ -539,6 +543,7 @@ struct Engine {
       const size_t budget = std::min<size_t>(free_b / 4, (size_t)16 << 30);
       const size_t per = std::max<size_t>((size_t)n_sens * 4, 4);
       frames_cap = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(n_frames, 1), budget / per));
+      if (const char *ev = getenv("FW25_FRAMES_CAP")) frames_cap = std::max(1, std::min(frames_cap, atoi(ev)));   // tests: small ring
       d_frames = dalloc<float>((size_t)frames_cap * std::max(n_sens, 1));
       // rim sensors read 0: the fused 2D step never writes their columns, so the ring starts out zeroed
       FW_CUDA(cudaMemsetAsync(d_frames, 0, (size_t)frames_cap * std::max(n_sens, 1) * sizeof(float), stream));
@@ -1228,26 +1233,127 @@ int run_multi(const fw25_problem *pb, const int32_t *device_ids, int n, float *g
 // helper threads fault the pages in (MADV_POPULATE_WRITE: contents untouched) while the GPU runs the time loop.
 struct Prefault {
   std::vector<std::thread> th;
+  char *lo = nullptr, *hi = nullptr;
+  size_t stripe = (size_t)16 << 20, n_stripes = 0;
+  std::atomic<size_t> next{0};
+  std::unique_ptr<std::atomic<unsigned char>[]> done;
+  size_t mark = 0;                       // stripes [0, mark) are known to be populated (reader side)
   void start(void *ptr, size_t bytes) {
 #ifdef MADV_POPULATE_WRITE
     if (!ptr || bytes < ((size_t)64 << 20)) return;
     if (const char *ev = getenv("FW25_PREFAULT")) { if (atoi(ev) == 0) return; }
     const size_t page = (size_t)sysconf(_SC_PAGESIZE);
-    char *lo = reinterpret_cast<char *>(((uintptr_t)ptr + page - 1) / page * page);
-    char *hi = reinterpret_cast<char *>(((uintptr_t)ptr + bytes) / page * page);
-    if (hi <= lo) return;
-    const int n = 4;
-    const size_t chunk = ((size_t)(hi - lo) / n + page - 1) / page * page;
-    for (int i = 0; i < n; ++i) {
-      char *a = lo + (size_t)i * chunk, *b = std::min(hi, a + chunk);
-      if (a < b) th.emplace_back([a, b] { (void)madvise(a, (size_t)(b - a), MADV_POPULATE_WRITE); });
-    }
+    lo = reinterpret_cast<char *>(((uintptr_t)ptr + page - 1) / page * page);
+    hi = reinterpret_cast<char *>(((uintptr_t)ptr + bytes) / page * page);
+    if (hi <= lo) { lo = hi = nullptr; return; }
+#ifdef MADV_HUGEPAGE
+    (void)madvise(lo, (size_t)(hi - lo), MADV_HUGEPAGE);   // 2 MB pages where the kernel allows: 512x fewer faults
+#endif
+    n_stripes = ((size_t)(hi - lo) + stripe - 1) / stripe;
+    done.reset(new std::atomic<unsigned char>[n_stripes]);
+    for (size_t i = 0; i < n_stripes; ++i) done[i].store(0);
+    // stripes are handed out in address order, so the front of the buffer -- the first frames -- is ready first
+    for (int i = 0; i < 6; ++i)
+      th.emplace_back([this] {
+        for (;;) {
+          const size_t k = next.fetch_add(1);
+          if (k >= n_stripes) return;
+          char *a = lo + k * stripe, *b = std::min(hi, a + stripe);
+          (void)madvise(a, (size_t)(b - a), MADV_POPULATE_WRITE);
+          done[k].store(1, std::memory_order_release);
+        }
+      });
 #else
     (void)ptr; (void)bytes;
 #endif
   }
+  // block until every page below `end` has been populated (no-op when nothing was started)
+  void wait_until(const void *end) {
+    if (!lo) return;
+    const char *e = std::min<const char *>(static_cast<const char *>(end), hi);
+    if (e <= lo) return;
+    const size_t need = ((size_t)(e - lo) + stripe - 1) / stripe;
+    while (mark < std::min(need, n_stripes)) {
+      if (done[mark].load(std::memory_order_acquire)) ++mark;
+      else std::this_thread::sleep_for(std::chrono::microseconds(50));
+    }
+  }
   void join() { for (auto &t : th) if (t.joinable()) t.join(); th.clear(); }
   ~Prefault() { join(); }
+};
+
+// Frames leave the device WHILE the time loop runs: whole-domain / whole-user-grid recordings (every shipped example)
+// produce gigabytes of frames, and copying them after the loop costs more than the loop itself (468 x 468 sensors every
+// 2nd step of 2805: loop 51 ms, copy 73 ms).  A copier thread waits for the event recorded after the steps that
+// complete a batch of frames and copies the batch out of the ring on its own stream; the loop only stalls when the
+// ring is full.  Single whole-grid engines (rows already in global order).
+struct FrameStreamer {
+  Engine &e;
+  float *genout;
+  Prefault &pf;
+  struct Job { int f0, f1; cudaEvent_t ev; };
+  std::deque<Job> q;
+  std::mutex m;
+  std::condition_variable cv_job, cv_done;
+  std::thread th;
+  bool closing = false, failed = false;
+  std::string err;
+  std::atomic<int> flushed{0};
+  double ms = 0;
+  cudaStream_t cs = nullptr;
+  FrameStreamer(Engine &e_, float *g, Prefault &p) : e(e_), genout(g), pf(p) {
+    FW_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    th = std::thread([this] { body(); });
+  }
+  void body() {
+    cudaSetDevice(e.device);
+    for (;;) {
+      Job j;
+      {
+        std::unique_lock<std::mutex> lk(m);
+        cv_job.wait(lk, [&] { return closing || !q.empty(); });
+        if (q.empty()) return;
+        j = q.front(); q.pop_front();
+      }
+      cudaError_t rc = cudaEventSynchronize(j.ev);
+      const size_t n = (size_t)e.n_sens;
+      pf.wait_until(genout + (size_t)j.f1 * n);
+      const auto t0 = std::chrono::steady_clock::now();
+      for (int f = j.f0; f < j.f1 && rc == cudaSuccess;) {          // the ring may wrap
+        const int slot = f % e.frames_cap, run = std::min(j.f1 - f, e.frames_cap - slot);
+        rc = cudaMemcpyAsync(genout + (size_t)f * n, e.d_frames + (size_t)slot * n, (size_t)run * n * 4,
+                             cudaMemcpyDeviceToHost, cs);
+        f += run;
+      }
+      if (rc == cudaSuccess) rc = cudaStreamSynchronize(cs);
+      ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+      cudaEventDestroy(j.ev);
+      {
+        std::lock_guard<std::mutex> lk(m);
+        if (rc != cudaSuccess) { failed = true; err = cudaGetErrorString(rc); }
+        flushed.store(j.f1);
+      }
+      cv_done.notify_all();
+    }
+  }
+  void push(int f0, int f1) {                                      // frames [f0, f1) are complete once the work queued so far is
+    cudaEvent_t ev = nullptr;
+    FW_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    FW_CUDA(cudaEventRecord(ev, e.stream));
+    { std::lock_guard<std::mutex> lk(m); q.push_back({f0, f1, ev}); }
+    cv_job.notify_one();
+  }
+  void wait_flushed(int upto) {
+    std::unique_lock<std::mutex> lk(m);
+    cv_done.wait(lk, [&] { return failed || flushed.load() >= upto; });
+  }
+  void close() {
+    { std::lock_guard<std::mutex> lk(m); closing = true; }
+    cv_job.notify_all();
+    if (th.joinable()) th.join();
+    if (cs) { cudaStreamDestroy(cs); cs = nullptr; }
+  }
+  ~FrameStreamer() { close(); }
 };
 
 // The time loop over an existing engine, from its current step to nT: frames are read out of the device ring when
@@ -1277,19 +1383,53 @@ void run_loop(Engine &e, float *genout, fw25_stats *stats, double setup_ms) {
     d2h_ms += ms;
     flushed = upto;
   };
+  // large recordings stream out while the loop runs (FrameStreamer); small ones are read at the end
+  const size_t frame_b = (size_t)e.n_sens * sizeof(float);
+  bool stream_out = e.n_sens > 0 && e.n_sens == e.n_sens_global && (size_t)e.n_frames * frame_b >= ((size_t)64 << 20);
+  if (const char *ev = getenv("FW25_STREAM_FRAMES")) {        // 0: never, 2: whenever there are frames (tests)
+    const int v = atoi(ev);
+    stream_out = v == 0 ? false : v == 2 ? (e.n_sens > 0 && e.n_sens == e.n_sens_global && e.n_frames > 0) : stream_out;
+  }
+  std::unique_ptr<FrameStreamer> fs;
+  if (stream_out) fs.reset(new FrameStreamer(e, genout, pf));
+  size_t batch_b = (size_t)32 << 20;
+  if (const char *ev = getenv("FW25_STREAM_BATCH_KB")) batch_b = (size_t)std::max(1, atoi(ev)) << 10;
+  const int batch = (int)std::max<size_t>(1, batch_b / std::max<size_t>(frame_b, 1));
+  int queued = 0;                                            // frames handed to the streamer
   FW_CUDA(cudaEventRecord(H.ev[0], e.stream));
   while (e.t < e.nT) {
     const int have = (e.t + e.modT - 1) / e.modT;            // frames recorded by steps 0 .. t-1
+    if (fs) {
+      int room = e.frames_cap - (have - fs->flushed.load());
+      if (room <= 0 && e.t % e.modT == 0) {                  // ring full: hand over what is complete, wait for space
+        if (have > queued) { fs->push(queued, have); queued = have; }
+        fs->wait_flushed(have - e.frames_cap / 2);             // until half of the ring is free again
+        if (fs->failed) fw25::fail(2, "frame streamer: " + fs->err);
+        room = e.frames_cap - (have - fs->flushed.load());
+      }
+      e.advance(e.nT - e.t, room);
+      const int now = (e.t + e.modT - 1) / e.modT;
+      if (now - queued >= batch) { fs->push(queued, now); queued = now; }
+      continue;
+    }
     int room = e.frames_cap - (have - flushed);
     if (room <= 0 && e.t % e.modT == 0) { const double b = d2h_ms; flush(have); flush_in_loop += d2h_ms - b; room = e.frames_cap; }
     e.advance(e.nT - e.t, room);
   }
   FW_CUDA(cudaEventRecord(H.ev[1], e.stream));
+  if (fs) {
+    if (e.n_frames > queued) fs->push(queued, e.n_frames);
+    fs->wait_flushed(e.n_frames);
+    if (fs->failed) fw25::fail(2, "frame streamer: " + fs->err);
+    fs->close();
+    d2h_ms = fs->ms;
+    flushed = e.n_frames;
+  }
   FW_CUDA(cudaEventSynchronize(H.ev[1]));
   FW_CUDA(cudaGetLastError());
   float loop_ms = 0;
   FW_CUDA(cudaEventElapsedTime(&loop_ms, H.ev[0], H.ev[1]));
-  flush(e.n_frames);
+  if (!fs) flush(e.n_frames);
   if (stats) {
     stats->setup_ms = setup_ms;
     stats->loop_ms = loop_ms - flush_in_loop;

@@ -100,3 +100,37 @@ def test_box_sensors_on_slabs_keep_global_order(built_lib):
     np.testing.assert_array_equal(lo_eng.local_sensor_ids(), np.arange(0, (cut - 10) * per_plane))
     np.testing.assert_array_equal(hi_eng.local_sensor_ids(), np.arange((cut - 10) * per_plane, 20 * per_plane))
     lo_eng.close(); hi_eng.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,cap,stream", [("het2d_long", 0, "2"), ("het2d_long", 7, "2"), ("het2d_long", 7, "0"),
+                                             ("het3d_long", 3, "2"), ("het2d_long", 1, "2")])
+def test_frames_streamed_during_the_loop_equal_frames_read_at_the_end(built_lib, name, cap, stream, monkeypatch):
+    """Large recordings leave the device while the time loop runs (FrameStreamer: copier thread, events, the loop
+    stalls only when the ring is full).  Forced on here for small problems, with small rings (wrap-around, ring-full
+    waits) and small batches; also the synchronous ring-full path (`stream` = "0")."""
+    pb = cases.make(name)
+    shape = pb.shape
+    pb.out_box = (0,) * pb.ndim + tuple(shape)          # whole-domain recording
+    pb.modT = 2
+    want = oracle.run(_listed(pb))
+    monkeypatch.setenv("FW25_STREAM_FRAMES", stream)
+    monkeypatch.setenv("FW25_STREAM_BATCH_KB", "64")
+    if cap:
+        monkeypatch.setenv("FW25_FRAMES_CAP", str(cap))
+    got, stats = engine.run(pb)
+    np.testing.assert_array_equal(got, want)
+    assert stats["d2h_bytes"] == want.nbytes and np.abs(want).max() > 0
+    with engine.Engine(pb) as e:                        # fw25_run_engine on a live engine, twice (transmit events)
+        a, _ = e.run()
+        e.reset(pb.icc, pb.icmat)
+        b, _ = e.run()
+    np.testing.assert_array_equal(a, want)
+    np.testing.assert_array_equal(b, want)
+
+
+def _listed(pb):
+    q = copy.copy(pb)
+    q.outc = pb.sensor_coords()
+    q.out_box = None
+    return q
