@@ -130,3 +130,26 @@ def test_spec_from_reference_like_pml_builder():
     assert spec.extended_shape == (47, 51) and spec.relax["d_x2_nu2"] is m["relax"]["d_x2_nu2"]
     want = -(2 + 1) * 1540.0 * np.log(1e-30) / (2 * (1e-4 * 5 + 1e-4 * 4))
     assert spec.d_target_pml() == want
+
+
+def test_spec_from_a_medium_with_lookup_database(tmp_path):
+    """A `fullwave.Medium` (alpha_coeff / alpha_power + path to the .mat database, medium.py:766-840): the spec reads
+    the database file the medium names, with the reference's schema (relaxation_parameters.py:147-155)."""
+    from types import SimpleNamespace as NS
+    from scipy.io import savemat
+    case = mc.CASES["m2d_lut"]
+    m = mc.medium_arrays(case)
+    lut = mc.synthetic_lut(case["lut"])
+    savemat(tmp_path / "db.mat", {"database": lut["database"], "alpha_0_list": lut["alpha_list"][None, :],
+                                  "power_list": lut["power_list"][None, :], "invalid_matrix": lut["invalid_matrix"]})
+    med = NS(sound_speed=m["sound_speed"], density=m["density"], beta=m["beta"], alpha_coeff=m["alpha_coeff"],
+             alpha_power=m["alpha_power"], path_relaxation_parameters_database=tmp_path / "db.mat",
+             relaxation_param_dict={})        # (a built Medium also carries this attribute: alpha_coeff decides)
+    pmlb = NS(medium_org=med, extended_grid=NS(dt=1e-8, dx=1e-4, c0=1540.0, cfl=0.2), m_spatial_order=8,
+              n_pml_layer=3, n_transition_layer=6)
+    spec = mapgen.MediumSpec.from_pml_builder(pmlb)
+    assert spec.relax is None and spec.alpha_power is m["alpha_power"]
+    np.testing.assert_array_equal(spec.lut.database, lut["database"])
+    np.testing.assert_array_equal(spec.lut.alpha_list, lut["alpha_list"])
+    np.testing.assert_array_equal(spec.lut.power_list, lut["power_list"])
+    assert spec.lut.invalid_matrix.shape == lut["invalid_matrix"].shape and spec.lut.invalid_matrix[-1, -1]
