@@ -151,6 +151,7 @@ struct Engine {
     if (stream) cudaStreamDestroy(stream);
   }
 
+  std::vector<float *> state_pool;   // state arrays allocated ahead, under the map uploads (init)
   double malloc_ms = 0;        // host time spent inside cudaMalloc (FW25_SETUP_TRACE=1 prints the setup phases)
   template <class T>
   T *dalloc(size_t n) {
@@ -384,15 +385,29 @@ struct Engine {
     for (auto m : maps)
       if (!m) fail(1, "a medium map pointer is NULL");
     if (!pb.dmap || !pb.dcmap) fail(1, "dmap / dcmap pointer is NULL");
-    F.rho = upload_map(maps[0], dev_maps, mp);
-    F.K = upload_map(maps[1], dev_maps, mp);
-    F.beta = upload_map(maps[2], dev_maps, mp);
-    F.kappax = upload_map(maps[3], dev_maps, mp);
-    F.kappau = upload_map(maps[4], dev_maps, mp);
-    F.ax1 = upload_map(maps[5], dev_maps, mp); F.bx1 = upload_map(maps[6], dev_maps, mp);
-    F.ax2 = upload_map(maps[7], dev_maps, mp); F.bx2 = upload_map(maps[8], dev_maps, mp);
-    F.au1 = upload_map(maps[9], dev_maps, mp); F.bu1 = upload_map(maps[10], dev_maps, mp);
-    F.au2 = upload_map(maps[11], dev_maps, mp); F.bu2 = upload_map(maps[12], dev_maps, mp);
+    // Host maps: every upload keeps the copy engine busy for tens of milliseconds, every cudaMalloc blocks this thread
+    // for about as long per 5 GB.  So the state arrays are allocated BETWEEN the uploads, under the copies in flight
+    // (at 800 x 1240 x 1240: 16 x 30 ms that used to follow the last upload).
+    const int n_state_needed = (pb.ext_p ? 0 : 1) + (pb.ext_u ? 0 : 1) + (pb.ext_v ? 0 : 1) +
+                               (ndim == 3 ? (pb.ext_w ? 0 : 1) + 12 : 8);
+    int uploads_done = 0;
+    auto up = [&](const float *src) {
+      const float *d = upload_map(src, dev_maps, mp);
+      ++uploads_done;
+      if (!dev_maps)
+        while ((int)state_pool.size() < std::min(n_state_needed, (n_state_needed * uploads_done + 12) / 13))
+          state_pool.push_back(dalloc<float>(cells));
+      return d;
+    };
+    F.rho = up(maps[0]);
+    F.K = up(maps[1]);
+    F.beta = up(maps[2]);
+    F.kappax = up(maps[3]);
+    F.kappau = up(maps[4]);
+    F.ax1 = up(maps[5]); F.bx1 = up(maps[6]);
+    F.ax2 = up(maps[7]); F.bx2 = up(maps[8]);
+    F.au1 = up(maps[9]); F.bu1 = up(maps[10]);
+    F.au2 = up(maps[11]); F.bu2 = up(maps[12]);
     for (int slot = 0; slot < 3; ++slot) {   // per-axis slots: alias the per-sweep maps unless truly anisotropic
       F.kv[slot] = F.kappax; F.kp[slot] = F.kappau;
       F.av[slot][0] = F.ax1; F.bv[slot][0] = F.bx1; F.av[slot][1] = F.ax2; F.bv[slot][1] = F.bx2;
@@ -437,7 +452,9 @@ struct Engine {
     trace_point("maps uploaded");
     // state
     auto state = [&](float *ext) {
-      float *d = ext ? ext : dalloc<float>(cells);
+      float *d = ext;
+      if (!d && !state_pool.empty()) { d = state_pool.back(); state_pool.pop_back(); }
+      if (!d) d = dalloc<float>(cells);
       FW_CUDA(cudaMemsetAsync(d, 0, cells * sizeof(float), stream));
       return d;
     };
