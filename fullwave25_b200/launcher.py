@@ -216,13 +216,13 @@ def install(fullwave_module=None, *, in_memory: bool = False, maps: str = "host"
     directory (`load_results=False`, exponential attenuation) fall through to the original method."""
     import importlib
     import weakref
+    if maps not in ("host", "device"):
+        raise ValueError('maps must be "host" or "device"')
     sol = importlib.import_module("fullwave.solver.solver")
     lau = importlib.import_module("fullwave.solver.launcher")
     saved = (sol.Launcher, lau.Launcher, sol.Solver.run, sol.PMLBuilder)
     sol.Launcher = Launcher
     lau.Launcher = Launcher
-    if maps not in ("host", "device"):
-        raise ValueError('maps must be "host" or "device"')
 
     if in_memory:
         original_run = sol.Solver.run

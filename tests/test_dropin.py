@@ -296,3 +296,37 @@ def test_patched_solver_run_in_memory(built_lib, shape):
                 undo()
             assert launcher._StaticSession.session is None
             assert fw.Solver.run.__module__.startswith("fullwave")
+
+
+@needs_ref
+def test_install_in_memory_patches_and_restores_the_reference(built_lib, tmp_path):
+    """CPU: `install(in_memory=True, maps="device")` swaps Launcher, `Solver.run` and the PMLBuilder `Solver.__init__`
+    instantiates; constructing a Solver then pads nothing; `uninstall()` puts everything back.  (Without a GPU the run
+    itself stops at the first CUDA call with the reference's error type.)"""
+    import importlib
+    from fullwave25_b200 import build, engine
+    sol = importlib.import_module("fullwave.solver.solver")
+    before = (sol.Launcher, sol.Solver.run, sol.PMLBuilder)
+    fw, grid, medium, source, sensor = ref_objects.build((20, 24), n_steps=30, n_sensors=9, n_air=3)
+    undo = launcher.install(in_memory=True, maps="device")
+    try:
+        assert sol.Launcher is launcher.Launcher and sol.Solver.run is not before[1]
+        assert issubclass(sol.PMLBuilder, before[2]) and sol.PMLBuilder is not before[2]
+        s = fw.Solver(tmp_path / "w", grid, medium, source, sensor, path_fullwave_simulation_bin=build.CLI,
+                      pml_layer_thickness_px=6, n_transition_layer=4)
+        assert s.pml_builder._full is None and s.pml_builder.extended_grid.nx == 20 + 2 * 18
+        try:
+            import torch
+            has_gpu = torch.cuda.is_available()
+        except Exception:  # noqa: BLE001
+            has_gpu = False
+        if not has_gpu:
+            with pytest.raises(launcher.SimulationError):
+                s.run()
+            assert s.pml_builder._full is None            # the device path never asked for the padded objects
+        with pytest.raises(ValueError):
+            launcher.install(maps="gpu")
+    finally:
+        undo()
+    assert (sol.Launcher, sol.Solver.run, sol.PMLBuilder) == before
+    assert engine.lib() is not None
