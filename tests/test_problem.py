@@ -111,3 +111,24 @@ def test_anisotropic_file_set_round_trip(tmp_path):
             np.testing.assert_array_equal(back.aniso[k], pb.aniso[k])
         iso = Problem.from_dat_dir(synthetic.make_problem(shape, nT=10).to_dat_dir(tmp_path / f"iso{pb.ndim}"))
         assert iso.aniso is None
+
+
+def test_problem_for_device_resident_maps():
+    """`Problem.for_device_maps`: only step counts, the stencil table and the point lists live on the host; the 13 maps
+    and dcmap are None and `normalise` leaves them alone (they sit in HBM, mapgen.MapSet)."""
+    from types import SimpleNamespace as NS
+    dmap = np.arange(9 * 2 * 3, dtype=np.float32).reshape(9, 2, 3)
+    ms = NS(shape=(30, 32, 34), ndmap=3, dmap=dmap, d_table=np.zeros((9, 2)))
+    grid = NS(nt=17, dx=1.25e-4, dt=1.5e-8, c0=1540.0)
+    src = NS(incoords=np.array([[9, 9, 9], [9, 9, 10]]), icmat=np.ones((2, 5)))
+    sen = NS(outcoords=np.array([[12, 13, 14]]), sampling_modulus_time=4)
+    pb = Problem.for_device_maps(ms, grid, src, sen, icczero=np.array([[20, 20, 20]]))
+    assert pb.rho is None and pb.dcmap is None and pb.dcmap_full3d
+    assert (pb.ndim, pb.nX, pb.nY, pb.nZ, pb.nT, pb.nTic, pb.modT, pb.ndmap) == (3, 30, 32, 34, 17, 5, 4, 3)
+    assert pb.icc.dtype == np.int32 and pb.icmat.dtype == np.float32 and pb.outc.shape == (1, 3)
+    assert pb.icczero.tolist() == [[20, 20, 20]] and pb.n_frames == 5
+    boxed = Problem.for_device_maps(ms, grid, src, NS(outcoords=None, sampling_modulus_time=2), out_box=(0, 0, 0, 30, 32, 34))
+    assert boxed.ncoordsout == 30 * 32 * 34 and boxed.outc.shape == (0, 3) and boxed.ncoordszero == 0
+    air = np.zeros((30, 32, 34), bool)
+    air[3, 4, 5] = True
+    assert Problem.for_device_maps(ms, grid, src, sen, air_map=air).icczero.tolist() == [[3, 4, 5]]
