@@ -39,6 +39,8 @@ UNIT = "Gpoint-updates/s"
 BYTES_PER_POINT = 208            # 27 (fd_u) + 25 (fd_p) float32 words per point-update
 BYTES_FD_U, BYTES_FD_P = 108, 100
 MEDIUM = dict(n_pml=36, n_trans=36, block=24, seed=1234, modT=4, n_sensors=1024, n_air=2000)
+WORKLOAD = ("synthetic3d_het_atten (BASELINE.json configs[4]: heterogeneous attenuating 3D medium, 3-layer plane source, "
+            "1024 point sensors every 4th step, 2000 air voxels; grid in config.grid_per_gpu)")
 
 
 def parse_grid(s):
@@ -341,66 +343,10 @@ def run_ours(args):
 
 # ------------------------------------------------------------------------------------------- reference
 def run_reference(args):
-    """The reference's shipped sm_100 executable through the reference's own launcher, on a bounded sample."""
-    rank = int(os.environ.get("RANK", 0))
-    if rank != 0:
-        return
-    world = args.gpus
-    K, W = args.steps, args.warmup
-    try:
-        from tools.ref_import import import_fullwave
-        import_fullwave(ROOT / "baseline" / "_ref")
-        from fullwave.solver.launcher import Launcher
-        from fullwave25_b200 import synthetic
-        from tools.make_ref_golden import REF_BIN
-    except Exception as e:  # noqa: BLE001
-        print(json.dumps({"impl": "reference", "unavailable": f"{type(e).__name__}: {e}"[:300]}))
-        return
-    sx, sy, sz = args.sample_grid
-    # bounded sample: the whole arm (host-side problem generation, the .dat directory, two runs of the binary) has to
-    # end within minutes, so beyond 2 GPUs the sample's global size is held at 2 x sample-grid planes
-    sx_gpu = sx if world <= 2 else max(48, (2 * sx) // world)
-    shape = (sx_gpu * world, sy, sz)
-    pb = synthetic.make_problem(shape, nT=W + K, modT=4, n_sensors=1024, n_air=2000, seed=1234, n_pml=36, n_trans=36,
-                                block=24)
-    work = Path("/dev/shm" if Path("/dev/shm").exists() else tempfile.gettempdir()) / "fw25_bench_ref"
-    import shutil
-    walls = []
-    try:
-        if work.exists():
-            shutil.rmtree(work)
-        pb.to_dat_dir(work)                                   # written once; the two runs differ in nT.dat only
-        shutil.copy(REF_BIN[3], work / REF_BIN[3].name)
-        (work / REF_BIN[3].name).chmod(0o755)
-        for nT in (W, W + K):
-            np.array(nT).astype(np.int32).tofile(work / "nT.dat")
-            (work / "genout.dat").unlink(missing_ok=True)
-            la = Launcher(work / REF_BIN[3].name, is_3d=True, use_gpu=True,
-                          cuda_device_id=list(range(world)) if world > 1 else 0)
-            t0 = time.perf_counter()
-            la.run(work, load_results=True)
-            walls.append(time.perf_counter() - t0)
-    except Exception as e:  # noqa: BLE001
-        print(json.dumps({"impl": "reference", "unavailable": f"{type(e).__name__}: {e}"[:300]}))
-        return
-    finally:
-        shutil.rmtree(work, ignore_errors=True)
-    dt = max(walls[1] - walls[0], 1e-9)
-    value = pb.n_points * K / dt / 1e9
-    sample = (f"reference sm_100 binary via fullwave.solver.launcher.Launcher on {shape[0]}x{sy}x{sz} "
-              f"(same medium recipe); {K} steps by differencing runs of nT={W} ({walls[0]:.2f} s) and "
-              f"nT={W + K} ({walls[1]:.2f} s) wall time incl. its file I/O")
-    print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": dt * 1e3 / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"synthetic3d_het_atten, bounded sample {sx_gpu}x{sy}x{sz} per GPU of BASELINE.json configs[4]",
-                   "parallelism": f"reference in-process x-slabs x{world}"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "kind": "reference", "cores": 1, "sample": sample,
-                         "note": "the reference has no CPU engine (solver.py:240-272): this is its shipped CUDA "
-                                 "engine, one host thread driving the GPU(s)"},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }), flush=True)
+    """The reference's shipped sm_100 executable through the reference's own launcher, timed per step from its
+    progress output (tools/bench_reference.py)."""
+    from tools import bench_reference
+    bench_reference.run_reference(args, metric=METRIC, unit=UNIT, workload=WORKLOAD, medium=MEDIUM)
 
 
 def main():
@@ -410,8 +356,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--grid", type=parse_grid, default=(800, 1240, 1240), help="extended grid PER GPU")
-    ap.add_argument("--sample-grid", type=parse_grid, default=(200, 416, 416),
-                    help="per-GPU extended grid of the reference arm's bounded sample")
+    ap.add_argument("--ref-planes", type=int, default=None,
+                    help="x planes per GPU of the reference arm's grid (default: the largest the reference can hold here)")
+    ap.add_argument("--no-ref-crosscheck", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -195,6 +195,20 @@ int main() {
   while (n_dev > 1 && pb.nX / n_dev < 2 * FW25_M) --n_dev;
   std::vector<int32_t> devs(n_dev);
   for (int i = 0; i < n_dev; ++i) devs[i] = i;
+  // FW25_DEVICE_LIST="0,0": explicit slab -> device assignment (tests: several slabs on ONE device, which
+  // CUDA_VISIBLE_DEVICES cannot express); slabs thinner than two halos are still refused by fw25_run
+  if (const char *dl = getenv("FW25_DEVICE_LIST")) {
+    devs.clear();
+    for (const char *q = dl; *q;) {
+      char *end = nullptr;
+      const long v = strtol(q, &end, 10);
+      if (end == q) break;
+      devs.push_back((int32_t)v);
+      q = *end == ',' ? end + 1 : end;
+    }
+    if (devs.empty()) devs.push_back(0);
+    n_dev = (int)devs.size();
+  }
   printf("fw25_engine: %d GPU(s)\n", n_dev);
   const int rc = fw25_run(&pb, devs.data(), n_dev, out_ptr, n_out, &st);
   if (rc != 0) {

@@ -36,13 +36,40 @@ def _profiles(n: int, n_pml: int, n_trans: int):
     return xi.astype(np.float32), tr.astype(np.float32)
 
 
+def _lists(nX, nY, nZ, nb, nTic, dt, dx, *, f0, c0, seed, n_sensors, n_air, source_layers, amp):
+    ys, zs = np.arange(nb, nY - nb, dtype=np.int32), np.arange(nb, nZ - nb, dtype=np.int32)
+    yy, zz = np.meshgrid(ys, zs, indexing="ij")
+    icc = np.concatenate([np.stack([np.full(yy.size, nb + l, np.int32), yy.ravel(), zz.ravel()], axis=1)
+                          for l in range(source_layers)])
+    pulse = synthetic.tone_burst(nTic, dt, f0, amp=amp).astype(np.float32)
+    rows = np.zeros((source_layers, nTic), np.float32)
+    for l in range(source_layers):
+        shift = int(round(l * dx / c0 / dt))
+        if shift < nTic:
+            rows[l, shift:] = pulse[: nTic - shift]
+    icmat = np.repeat(rows, yy.size, axis=0)
+    rng = np.random.default_rng(seed)
+
+    def pick(n):
+        x = rng.integers(nb + source_layers, nX - nb, size=n)
+        y = rng.integers(nb, nY - nb, size=n)
+        z = rng.integers(nb, nZ - nb, size=n)
+        flat = np.unique((x.astype(np.int64) * nY + y) * nZ + z)
+        return np.stack(np.unravel_index(flat, (nX, nY, nZ)), axis=1).astype(np.int32)
+
+    outc = pick(n_sensors)
+    icczero = pick(n_air) if n_air else np.zeros((0, 3), np.int32)
+    return icc, icmat, outc, icczero
+
+
 def make_slab(global_shape, gx0: int, gx1: int, *, device, nT: int, f0: float = 1e6, c0: float = 1540.0,
               ppw: int = 12, cfl: float = 0.2, n_pml: int = 36, n_trans: int = 36, block: int = 24,
               seed: int = 1234, modT: int = 4, n_sensors: int = 1024, n_air: int = 2000,
-              source_layers: int = 3, amp: float = 1e5, chunk: int = 8):
+              source_layers: int = 3, amp: float = 1e5, chunk: int = 8, with_lists: bool = True):
     """Returns (pb, maps): pb is a Problem holding the scalars, stencil table and the GLOBAL coordinate
     lists (its map fields are None); maps = {name: torch tensor [gx1-gx0, nY, pitch]} incl. "dcmap"
-    (int32) and "pitch".  Planes are global x in [gx0, gx1)."""
+    (int32) and "pitch".  Planes are global x in [gx0, gx1).  with_lists=False leaves the coordinate lists empty
+    (callers that generate a grid slab by slab need them once)."""
     import torch
 
     nX, nY, nZ = (int(s) for s in global_shape)
@@ -118,29 +145,13 @@ def make_slab(global_shape, gx0: int, gx1: int, *, device, nT: int, f0: float = 
     dmap = stencil.d_map(float(C_MIN), dim, dt, dx, is_3d=True).astype(np.float32)
 
     # coordinate lists (GLOBAL, row-major like np.where): plane source, point sensors, air voxels
-    ys, zs = np.arange(nb, nY - nb, dtype=np.int32), np.arange(nb, nZ - nb, dtype=np.int32)
-    yy, zz = np.meshgrid(ys, zs, indexing="ij")
-    icc = np.concatenate([np.stack([np.full(yy.size, nb + l, np.int32), yy.ravel(), zz.ravel()], axis=1)
-                          for l in range(source_layers)])
     nTic = min(nT, int(np.ceil(2.0 / f0 / dt)) + 1)
-    pulse = synthetic.tone_burst(nTic, dt, f0, amp=amp).astype(np.float32)
-    rows = np.zeros((source_layers, nTic), np.float32)
-    for l in range(source_layers):
-        shift = int(round(l * dx / c0 / dt))
-        if shift < nTic:
-            rows[l, shift:] = pulse[: nTic - shift]
-    icmat = np.repeat(rows, yy.size, axis=0)
-    rng = np.random.default_rng(seed)
-
-    def pick(n):
-        x = rng.integers(nb + source_layers, nX - nb, size=n)
-        y = rng.integers(nb, nY - nb, size=n)
-        z = rng.integers(nb, nZ - nb, size=n)
-        flat = np.unique((x.astype(np.int64) * nY + y) * nZ + z)
-        return np.stack(np.unravel_index(flat, (nX, nY, nZ)), axis=1).astype(np.int32)
-
-    outc = pick(n_sensors)
-    icczero = pick(n_air) if n_air else np.zeros((0, 3), np.int32)
+    if with_lists:
+        icc, icmat, outc, icczero = _lists(nX, nY, nZ, nb, nTic, dt, dx, f0=f0, c0=c0, seed=seed, n_sensors=n_sensors,
+                                           n_air=n_air, source_layers=source_layers, amp=amp)
+    else:
+        icc = outc = icczero = np.zeros((0, 3), np.int32)
+        icmat = np.zeros((0, nTic), np.float32)
 
     none = {name: None for name in MAP_NAMES}
     pb = Problem(ndim=3, nX=nXl, nY=nY, nZ=nZ, nT=nT, nTic=nTic, modT=modT, ndmap=dim + 1,

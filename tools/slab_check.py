@@ -23,14 +23,17 @@ from tests.test_slab import _problem
 
 def local_main(case, n, mode="native"):
     """Single process, n devices: engine.run(pb, device_ids=[0..n-1]) == the reference's cuda_device_id list.
-    mode "native": fw25_run's own multi-device runner (C++); "torch": the Python lockstep driver (runtime.run_local)."""
+    mode "native": fw25_run's own multi-device runner (C++); "torch": the Python lockstep driver (runtime.run_local).
+    FW25_TEST_DEVICES="0,0" maps the n slabs onto the listed devices (several slabs on one GPU)."""
     from fullwave25_b200 import engine, runtime
     from oracle import oracle
     pb = _problem(case)
+    ids = [int(v) for v in os.environ["FW25_TEST_DEVICES"].split(",")] if os.environ.get("FW25_TEST_DEVICES") else list(range(n))
+    n = len(ids)
     if mode == "torch":
-        got, stats = runtime.run_local(pb, list(range(n)), return_stats=True)
+        got, stats = runtime.run_local(pb, ids, return_stats=True)
     else:
-        got, stats = engine.run(pb, device_ids=tuple(range(n)))
+        got, stats = engine.run(pb, device_ids=tuple(ids))
     want = oracle.run(pb)
     print("SLABCHECK " + json.dumps({"case": case, "world": n, "mode": "in-process " + mode,
                                      "bit_exact": bool(np.array_equal(got, want)), "n_devices": int(stats.get("n_devices", 0)),
