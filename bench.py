@@ -125,12 +125,39 @@ def host_setup_baseline() -> dict | None:
         return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
 
 
+def parity_problem(world: int):
+    """A mid-size problem for the N-vs-1 bit-identity check that precedes the timed runs: >= 3 x-marching chunks per
+    slab, source cells, sensors and air voxels ON both sides of every interface (ghost-plane injection, sensor
+    ownership) and in the planes the halo carries."""
+    from fullwave25_b200 import synthetic
+    from fullwave25_b200.slab import partition
+    pb = synthetic.make_problem((world * 100, 56, 64), nT=40, modT=2, seed=77, n_pml=6, n_trans=4, n_sensors=256,
+                                n_air=64)
+    rng = np.random.default_rng(7)
+    out, air, src = [], [], []
+    for sl in partition(pb.nX, world)[:-1]:
+        e = sl.own_hi
+        for x in (e - 8, e - 1, e, e + 7):
+            yz = rng.integers(20, 34, size=(8, 2))
+            out += [(x, y, z) for y, z in yz]
+            air.append((x, int(yz[0, 0]) + 1, int(yz[0, 1]) + 2))
+            src.append((x, int(yz[1, 0]) - 1, int(yz[1, 1]) + 3))
+    pb.outc = np.concatenate([pb.outc, np.asarray(out, np.int32).reshape(-1, 3)])
+    pb.icczero = np.concatenate([pb.icczero, np.asarray(air, np.int32).reshape(-1, 3)])
+    pb.icc = np.concatenate([pb.icc, np.asarray(src, np.int32).reshape(-1, 3)])
+    pb.icmat = np.concatenate([pb.icmat, np.repeat(0.5 * pb.icmat[:1], len(src), axis=0)])
+    return pb.normalise(), len(out), len(src)
+
+
 def run_ours(args):
+    import hashlib
+
     import torch
     import torch.distributed as dist
     from fullwave25_b200 import engine, synthetic_device
     from fullwave25_b200.runtime import SlabEngine, TorchComm, gather_frames
     from fullwave25_b200.slab import SlabDriver, partition
+    from tools.bench_reference import choose_planes, ref_nT
 
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -142,25 +169,14 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     engine.lib()                                          # fail loudly if libfw25.so is missing
-
-    nXl, nY, nZ = args.grid
-    gshape = (nXl * world, nY, nZ)
-    slab = partition(gshape[0], world)[rank]
-    K, W = args.steps, args.warmup
-    nT = W + K
-    t_gen = time.perf_counter()
-    pb, maps = synthetic_device.make_slab(gshape, slab.gx0, slab.gx1, device=dev, nT=nT, **MEDIUM)
-    torch.cuda.synchronize()
-    t_gen = time.perf_counter() - t_gen
-    dmaps = {k: (v if k == "pitch" else v.data_ptr()) for k, v in maps.items()}
-
-    eng = SlabEngine(pb, slab, dev, device_maps=dmaps)
-    comm = TorchComm(dist if world > 1 else None)
+    D = dist if world > 1 else None
+    comm = TorchComm(D)
     main = torch.cuda.Stream(dev)
     bnd = torch.cuda.Stream(dev, priority=-1)
-    drv = SlabDriver(slab, eng, comm, pb.modT, streams=(main, bnd), ndim=3)
-    pts_step = gshape[0] * nY * nZ                        # whole-job points per step (extended grid)
-    pts_rank = (slab.own_hi - slab.own_lo) * nY * nZ
+    nXl, nY, nZ = args.grid
+    K, W = args.steps, args.warmup
+    peak, peak_src = peaks()
+    same_planes, _ = choose_planes(world, nY, nZ, args.ref_planes)      # before this process pins any host memory
 
     def barrier():
         torch.cuda.synchronize()
@@ -168,12 +184,66 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return float(x)
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(drv, n):
+        """n steps between CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks."""
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(main)
+        for _ in range(n):
+            drv.step()
+        drv.finish()
+        b.record(main)
+        barrier()
+        return max_over_ranks(a.elapsed_time(b))
+
+    def resident(gshape, nT, *, full3d=True):
+        """Slab engine of this rank over device-generated maps of `gshape` (maps adopted in place)."""
+        slab = partition(gshape[0], world)[rank]
+        t0 = time.perf_counter()
+        pb, maps = synthetic_device.make_slab(gshape, slab.gx0, slab.gx1, device=dev, nT=nT, **MEDIUM)
+        torch.cuda.synchronize()
+        t_gen = time.perf_counter() - t0
+        pb.dcmap_full3d = full3d
+        dmaps = {k: (v if k == "pitch" else v.data_ptr()) for k, v in maps.items()}
+        eng = SlabEngine(pb, slab, dev, device_maps=dmaps)
+        drv = SlabDriver(slab, eng, comm, pb.modT, streams=(main, bnd), ndim=3)
+        return slab, pb, maps, eng, drv, t_gen
+
+    # ---- (0) N ranks == 1 rank, bit for bit, before anything is timed (mid-size grid, everything on the interfaces)
+    parity = None
+    if world > 1:
+        pbp, n_if_sens, n_if_src = parity_problem(world)
+        slab = partition(pbp.nX, world)[rank]
+        engp = SlabEngine(pbp.slab(slab.gx0, slab.gx1).normalise(), slab, dev)
+        drvp = SlabDriver(slab, engp, comm, pbp.modT, streams=(main, bnd), ndim=3)
+        for _ in range(pbp.nT):
+            drvp.step()
+        got = gather_frames(drvp, engp, pbp.n_frames, pbp.ncoordsout, D)
+        engp.close()
+        if rank == 0:
+            one, _ = engine.run(pbp, device_ids=(local,))
+            parity = {"grid": "x".join(map(str, pbp.shape)), "steps": pbp.nT, "frames": pbp.n_frames,
+                      "sensors": pbp.ncoordsout, "sensors_on_interfaces": n_if_sens, "sources_on_interfaces": n_if_src,
+                      "identical": bool(np.array_equal(got, one)), "absmax": float(np.abs(one).max()),
+                      "what": f"{world} ranks (NCCL halos) vs rank 0 alone, all sensor frames, same bits"}
+        barrier()
+
+    # ---- (1) headline: K steps on the full-size grid, maps resident in HBM
+    gshape = (nXl * world, nY, nZ)
+    slab, pb, maps, eng, drv, t_gen = resident(gshape, W + K)
+    pts_step = gshape[0] * nY * nZ                        # whole-job points per step (extended grid)
+    pts_rank = (slab.own_hi - slab.own_lo) * nY * nZ
     for _ in range(W):
         drv.step()
     drv.finish()
     barrier()
-
-    # ---- timed region: K steps, CUDA events on the launching stream, max over ranks
     sampler = ClockSampler(local) if rank == 0 else None
     l0 = eng.eng.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -197,15 +267,12 @@ def run_ours(args):
     ev1.record(main)
     barrier()
     clocks = sampler.stop() if sampler else None
-    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms = float(ms.item())
+    ms = max_over_ranks(ev0.elapsed_time(ev1))
     launches = eng.eng.launches - l0
     value = pts_step * K / (ms * 1e-3) / 1e9
+    # frames of steps 0 .. W+K-1 BEFORE anything else touches the ring (the halo-exposure loop below runs extra steps)
+    frames_resident = gather_frames(drv, eng, pb.n_frames, pb.ncoordsout, D)
 
-    peak, peak_src = peaks()
-    roof = None
     if world == 1:
         u_ms = sum(e[0].elapsed_time(e[1]) for e in kev) / K
         p_ms = sum(e[2].elapsed_time(e[3]) for e in kev) / K
@@ -217,128 +284,185 @@ def run_ours(args):
                 "fd_u": {"ms": u_ms, "GBps": pts_rank * BYTES_FD_U / (u_ms * 1e-3) / 1e9},
                 "fd_p": {"ms": p_ms, "GBps": pts_rank * BYTES_FD_P / (p_ms * 1e-3) / 1e9},
                 "step": {"GBps": value * BYTES_PER_POINT / world, "frac": value * BYTES_PER_POINT / world / peak}}
-        prof = ROOT / "profiles" / "traffic_r01.json"       # dram bytes per launch from the committed ncu capture
-        if prof.exists():
-            try:
-                tr = json.loads(prof.read_text())
-                roof["traffic"] = tr.get("fd_u" if u_ms >= p_ms else "fd_p", {}).get("dram_bytes_per_point", 0) * pts_rank or None
-                roof["traffic_source"] = ("dram__bytes_read.sum + dram__bytes_write.sum per point from " + str(tr.get("source"))
-                                          + ", scaled to this launch's points")
-            except Exception:  # noqa: BLE001
-                pass
+        roof.update(traffic_from_profile("fd_u" if u_ms >= p_ms else "fd_p", (nXl, nY, nZ)))
     else:
         roof = {"bound": "hbm", "kernel": "whole step (fd_u + fd_p + halo exchange), per GPU",
                 "achieved": value * BYTES_PER_POINT / world, "peak": peak, "unit": "GB/s",
                 "frac": value * BYTES_PER_POINT / world / peak, "traffic": None, "peak_source": peak_src}
 
-    # ---- halo cost exposed: same K' steps with the transfers skipped (results invalid, timing only)
+    # ---- (2) halo cost exposed: the same steps with the transfers skipped (results invalid from here on, timing only)
     halo = None
     if world > 1:
         Kh = min(K, 20)
-        t_on, t_off = [], []
-        for flag, acc in ((True, t_on), (False, t_off)):
-            drv.exchange_enabled = flag
-            barrier()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(main)
-            for _ in range(Kh):
-                drv.step()
-            drv.finish()
-            b.record(main)
-            barrier()
-            x = torch.tensor([a.elapsed_time(b)], device=dev, dtype=torch.float64)
-            dist.all_reduce(x, op=dist.ReduceOp.MAX)
-            acc.append(float(x.item()) / Kh)
+        t_on = timed(drv, Kh) / Kh
+        drv.exchange_enabled = False
+        t_off = timed(drv, Kh) / Kh
         drv.exchange_enabled = True
-        planes = 18 * (int(slab.has_lo) + int(slab.has_hi))
-        halo = {"exposed_ms_per_step": t_on[0] - t_off[0], "ms_per_step_with": t_on[0], "ms_per_step_without": t_off[0],
-                "bytes_per_step_per_interface_direction": 18 * nY * int(maps["pitch"]) * 4, "planes_sent_rank0": planes}
+        halo = {"exposed_ms_per_step": t_on - t_off, "ms_per_step_with": t_on, "ms_per_step_without": t_off,
+                "bytes_per_step_per_interface_direction": 18 * nY * int(maps["pitch"]) * 4,
+                "planes_sent_rank0": 18 * (int(slab.has_lo) + int(slab.has_hi))}
+    config = {"workload": WORKLOAD, "grid_per_gpu": f"{nXl}x{nY}x{nZ}", "global_grid": "x".join(map(str, gshape)),
+              "parallelism": f"x-slab x{world}", "points_per_step": pts_step,
+              "l2": "every array is >> L2 (126 MB): no flush between steps",
+              "medium_generation_s": round(t_gen, 2), "sensors": int(pb.ncoordsout), "sources": int(pb.ncoords),
+              "air_voxels": int(pb.ncoordszero), "ndmap": int(pb.ndmap), "dcmap": "per-voxel (dcmap_full3d=1)"}
+    pb_full, maps_full = pb, maps
+    eng.close()
+    del eng, drv, maps
 
-    # ---- end to end through the public API: pinned HOST maps -> upload -> K steps -> sensor frames on the host
-    # sensor frames of the resident run (steps 0 .. W+K-1): the end-to-end run below repeats steps 0 .. K-1 from HOST
-    # maps through another upload path, so its frames must be the same bits -- a full-size parity property
-    frames_chk = gather_frames(drv, eng, pb.n_frames, pb.ncoordsout, dist if world > 1 else None)
+    def free_device():
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+
+    # ---- (3) strong scaling: the ONE-GPU grid split over the N GPUs (BASELINE.json configs[4] "weak and strong")
+    strong = None
+    if world > 1 and not args.no_strong:
+        del maps_full
+        maps_full = None
+        free_device()
+        sshape = (nXl, nY, nZ)
+        s_slab, s_pb, s_maps, s_eng, s_drv, _ = resident(sshape, W + K)
+        timed(s_drv, W)
+        s_ms = timed(s_drv, K)
+        s_drv.exchange_enabled = False
+        s_off = timed(s_drv, min(K, 20)) / min(K, 20)
+        strong = {"scaling": "strong", "global_grid": "x".join(map(str, sshape)),
+                  "planes_per_gpu": s_slab.own_hi - s_slab.own_lo, "boundary_planes_per_gpu":
+                  sum(hi - lo for lo, hi in s_drv._boundary_ranges()),
+                  "value": nXl * nY * nZ * K / (s_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": s_ms / K,
+                  "ms_per_step_without_transfers": s_off, "exposed_halo_ms_per_step": s_ms / K - s_off,
+                  "roofline_frac_per_gpu": nXl * nY * nZ * K / (s_ms * 1e-3) * BYTES_PER_POINT / world / 1e9 / peak}
+        s_eng.close()
+        del s_eng, s_drv, s_maps
+
+    # ---- (4) the grid the reference arm runs (the largest it can hold), in the reference binary's own dcmap mode,
+    #          same nT: the sha256 of the sensor frames must equal the one the reference arm prints
+    same = None
+    if same_planes and not args.no_same_grid:
+        maps_full = None
+        free_device()
+        nTs = ref_nT(W, K, MEDIUM["modT"])
+        g2 = (same_planes * world, nY, nZ)
+        _, g_pb, g_maps, g_eng, g_drv, _ = resident(g2, nTs, full3d=False)
+        timed(g_drv, W)
+        g_ms = timed(g_drv, K)
+        for _ in range(nTs - W - K):
+            g_drv.step()
+        fr = gather_frames(g_drv, g_eng, g_pb.n_frames, g_pb.ncoordsout, D)
+        same = {"grid_per_gpu": f"{same_planes}x{nY}x{nZ}", "global_grid": "x".join(map(str, g2)),
+                "value": g2[0] * nY * nZ * K / (g_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": g_ms / K,
+                "dcmap": "reference 3D binary mode (dcmap_full3d=0)", "nT": nTs,
+                "genout_sha256": hashlib.sha256(np.ascontiguousarray(fr, np.float32).tobytes()).hexdigest()
+                if fr is not None else None,
+                "note": "same inputs, steps and sensor list as `bench.py --impl reference`: its genout_sha256 must match"}
+        g_eng.close()
+        del g_eng, g_drv, g_maps
+        free_device()
+
+    # ---- (5) end to end through the public API from HOST buffers
     e2e = None
     if not args.no_e2e:
-        import psutil
-        need = 14 * slab.n_local * nY * nZ * 4
-        avail = psutil.virtual_memory().available / max(world, 1)
-        e_nXl = nXl
-        if need * 1.25 > avail:                           # host RAM bound: shrink the e2e slab, say so
-            e_nXl = max(64, int(nXl * avail / (need * 1.25)) // 8 * 8)
-        eng.close()
-        del eng, drv
-        if e_nXl != nXl:
-            del maps
-            torch.cuda.empty_cache()
-            gshape_e = (e_nXl * world, nY, nZ)
-            slab_e = partition(gshape_e[0], world)[rank]
-            pb_e, maps_e = synthetic_device.make_slab(gshape_e, slab_e.gx0, slab_e.gx1, device=dev, nT=K, **MEDIUM)
-        else:
-            gshape_e, slab_e, pb_e, maps_e = gshape, slab, pb, maps
-            pb_e.nT = K
-            pb_e.nTic = min(pb_e.nTic, K)
-            pb_e.icmat = np.ascontiguousarray(pb_e.icmat[:, : pb_e.nTic])
-        host = synthetic_device.maps_to_host(maps_e, nZ, pin=True)
-        del maps_e
-        if e_nXl == nXl:
-            del maps
-        torch.cuda.empty_cache()
-        import dataclasses
-        pb_h = dataclasses.replace(pb_e, **{k: v.numpy() for k, v in host.items()})
-        icm = torch.empty(pb_h.icmat.shape, dtype=torch.float32, pin_memory=True)   # the source signals are inputs too
-        icm.numpy()[...] = pb_h.icmat
-        pb_h.icmat = icm.numpy()
-        h2d = sum(v.numel() * 4 for v in host.values()) + pb_h.icmat.nbytes + pb_h.icc.nbytes
-        barrier()
-        t0 = time.perf_counter()
-        eng2 = SlabEngine(pb_h, slab_e, dev)                # H2D of the 14 maps + coordinate lists happens here
-        eng2.eng.sync()
-        t_setup = time.perf_counter() - t0                  # allocation + upload (part of the timed region)
-        drv2 = SlabDriver(slab_e, eng2, comm, pb_h.modT, streams=(main, bnd))
-        for _ in range(K):
-            drv2.step()
-        out = gather_frames(drv2, eng2, pb_h.n_frames, pb_h.ncoordsout, dist if world > 1 else None)
-        barrier()
-        dt = time.perf_counter() - t0
-        x = torch.tensor([dt], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(x, op=dist.ReduceOp.MAX)
-        dt = float(x.item())
-        d2h = pb_h.n_frames * eng2.eng.n_local_sensors * 4
-        e2e = {"value": gshape_e[0] * nY * nZ * K / dt / 1e9, "unit": UNIT,
-               "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K, "seconds": dt,
-               "setup_seconds": t_setup, "upload_GBps": h2d / t_setup / 1e9,
-               "grid_per_gpu": f"{e_nXl}x{nY}x{nZ}", "launches": eng2.eng.launches,
-               "finite": bool(np.isfinite(out).all()) if out is not None else None,
-               "frames_identical_to_resident_run": (bool(np.array_equal(out, frames_chk[: out.shape[0]]))
-                                                    if out is not None and frames_chk is not None and e_nXl == nXl
-                                                    else None),
-               "absmax": float(np.abs(out).max()) if out is not None and out.size else None,
-               "api": "fullwave25_b200.runtime.SlabEngine(host maps) + SlabDriver.step + gather_frames"}
-        eng2.close()
+        e2e = run_e2e(args, rank, world, dev, comm, (main, bnd), pb_full, maps_full, frames_resident, barrier, max_over_ranks)
 
     if rank == 0:
+        config["same_grid"] = same
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"synthetic3d_het_atten {nXl}x{nY}x{nZ} extended points per GPU "
-                                   f"(BASELINE.json configs[4]; global {gshape[0]}x{nY}x{nZ})",
-                       "parallelism": f"x-slab x{world}", "points_per_step": pts_step,
-                       "l2": "every array is >> L2 (126 MB): no flush between steps",
-                       "medium_generation_s": round(t_gen, 2), "sensors": int(pb.ncoordsout), "sources": int(pb.ncoords),
-                       "air_voxels": int(pb.ncoordszero), "ndmap": int(pb.ndmap), "dcmap": "per-voxel (dcmap_full3d=1)"},
+            "dtype": "f32", "data": "synthetic", "config": config,
             "roofline": roof, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
         if halo:
             line["halo"] = halo
+        if strong:
+            line["strong"] = strong
+        if parity:
+            line["parity_n_vs_1"] = parity
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
             line["host_setup_baseline"] = host_setup_baseline()
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def traffic_from_profile(kernel: str, grid) -> dict:
+    """roofline.traffic: dram__bytes_read.sum + dram__bytes_write.sum of the committed `ncu --set full` capture, per
+    UPDATED point (the 8-cell rim is never touched), scaled to the updated points of this launch."""
+    for name in ("traffic_r02.json", "traffic_r01.json"):
+        prof = ROOT / "profiles" / name
+        if not prof.exists():
+            continue
+        try:
+            tr = json.loads(prof.read_text())
+            upd = (grid[0] - 16) * (grid[1] - 16) * (grid[2] - 16)
+            per = tr.get(kernel, {}).get("dram_bytes_per_updated_point")
+            if per is None:
+                continue
+            return {"traffic": per * upd, "traffic_per_updated_point": per, "updated_points_per_launch": upd,
+                    "algorithmic_bytes_per_updated_point": BYTES_FD_U if kernel == "fd_u" else BYTES_FD_P,
+                    "traffic_source": f"profiles/{name}: {tr.get('source')}"}
+        except Exception:  # noqa: BLE001
+            pass
+    return {}
+
+
+def run_e2e(args, rank, world, dev, comm, streams, pb, maps, frames_chk, barrier, max_over_ranks):
+    """The same job through the public API with HOST buffers: pinned host maps -> upload -> K steps -> frames."""
+    import dataclasses
+
+    import psutil
+    import torch
+    import torch.distributed as dist
+    from fullwave25_b200 import synthetic_device
+    from fullwave25_b200.runtime import SlabEngine, gather_frames
+    from fullwave25_b200.slab import SlabDriver, partition
+    D = dist if world > 1 else None
+    main, bnd = streams
+    nXl, nY, nZ = args.grid
+    K = args.steps
+    gshape = (nXl * world, nY, nZ)
+    slab = partition(gshape[0], world)[rank]
+    if maps is None:
+        pb, maps = synthetic_device.make_slab(gshape, slab.gx0, slab.gx1, device=dev, nT=K, **MEDIUM)
+    need = 14 * slab.n_local * nY * nZ * 4
+    avail = psutil.virtual_memory().available / max(world, 1)
+    if need * 1.25 > avail:
+        return {"unavailable": f"host RAM: {need / 1e9:.0f} GB of pinned maps per rank, {avail / 1e9:.0f} GB available"}
+    pb = dataclasses.replace(pb, nT=K, nTic=min(pb.nTic, K))
+    pb.icmat = np.ascontiguousarray(pb.icmat[:, : pb.nTic])
+    host = synthetic_device.maps_to_host(maps, nZ, pin=True)
+    del maps
+    torch.cuda.empty_cache()
+    pb_h = dataclasses.replace(pb, **{k: v.numpy() for k, v in host.items()})
+    icm = torch.empty(pb_h.icmat.shape, dtype=torch.float32, pin_memory=True)   # the source signals are inputs too
+    icm.numpy()[...] = pb_h.icmat
+    pb_h.icmat = icm.numpy()
+    h2d = sum(v.numel() * 4 for v in host.values()) + pb_h.icmat.nbytes + pb_h.icc.nbytes
+    barrier()
+    t0 = time.perf_counter()
+    eng2 = SlabEngine(pb_h, slab, dev)                  # H2D of the 14 maps + coordinate lists happens here
+    eng2.eng.sync()
+    t_setup = time.perf_counter() - t0                  # allocation + upload (part of the timed region)
+    drv2 = SlabDriver(slab, eng2, comm, pb_h.modT, streams=(main, bnd))
+    for _ in range(K):
+        drv2.step()
+    out = gather_frames(drv2, eng2, pb_h.n_frames, pb_h.ncoordsout, D)
+    barrier()
+    dt = max_over_ranks(time.perf_counter() - t0)
+    d2h = pb_h.n_frames * eng2.eng.n_local_sensors * 4
+    e2e = {"value": gshape[0] * nY * nZ * K / dt / 1e9, "unit": UNIT,
+           "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K, "seconds": dt,
+           "setup_seconds": t_setup, "upload_GBps": h2d / t_setup / 1e9,
+           "grid_per_gpu": f"{nXl}x{nY}x{nZ}", "launches": eng2.eng.launches,
+           "finite": bool(np.isfinite(out).all()) if out is not None else None,
+           "frames_identical_to_resident_run": (bool(np.array_equal(out, frames_chk[: out.shape[0]]))
+                                                if out is not None and frames_chk is not None else None),
+           "absmax": float(np.abs(out).max()) if out is not None and out.size else None,
+           "api": "fullwave25_b200.runtime.SlabEngine(host maps) + SlabDriver.step + gather_frames"}
+    eng2.close()
+    return e2e
 
 
 # ------------------------------------------------------------------------------------------- reference
@@ -360,6 +484,8 @@ def main():
                     help="x planes per GPU of the reference arm's grid (default: the largest the reference can hold here)")
     ap.add_argument("--no-ref-crosscheck", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-strong", action="store_true")
+    ap.add_argument("--no-same-grid", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:

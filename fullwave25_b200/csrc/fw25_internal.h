@@ -88,6 +88,20 @@ bool sweeps2d_fusable();
 int launch_sweep_p_2d_fused(const Plan2D *pl, const Fields &F, const Geom &G, int a_lo, int a_hi, cudaStream_t st,
                             const Fuse2D &X, int t_off, int flags);
 
+// streamed map generation (fw25_mapgen.cu): blocks of `block_planes` extended planes become valid in x order while the
+// caller already steps.  mapstream_wait_recorded blocks the HOST until the block's event has been recorded and returns
+// it (nullptr + g_err if the uploader failed); mapstream_finish joins the uploader and hands over the map set.
+struct MapStream;
+}  // namespace fw25
+struct fw25_medium;
+struct fw25_mapset;
+namespace fw25 {
+MapStream *mapstream_start(const fw25_medium *md, int device, int block_planes, fw25_mapset **ms_out);
+int mapstream_blocks(const MapStream *S);
+cudaEvent_t mapstream_wait_recorded(MapStream *S, int block);
+fw25_mapset *mapstream_finish(MapStream *S, double *stats_ms, int64_t *h2d_bytes);
+void mapstream_destroy(MapStream *S);
+
 // point kernels: fw25_points.cu
 void launch_dcmap_mask(int32_t *dcmap, long long cells, int pitch, int nC, int nB, long long first_plane,
                        long long limit, cudaStream_t st);
@@ -100,6 +114,12 @@ void launch_record_dev(const float *p, const long long *sens_idx, int n_sens, fl
                        int modT, int cap, cudaStream_t st);
 void launch_record_box(const float *p, float *frames, long long n_sens, const int *d_t, int t_off, int modT, int cap,
                        const SensBox &B, cudaStream_t st);
+// plane-range forms (time-skewed start): entries outside local planes [a_lo, a_hi) are left alone
+void launch_inject_range(float *p, const long long *src_idx, const int *src_row, const unsigned char *src_flag, int n_src,
+                         const float *icmat, int nTic, int t, const long long *air_idx, int n_air, long long sA, int a_lo,
+                         int a_hi, cudaStream_t st);
+void launch_record_range(const float *p, const long long *sens_idx, int n_sens, float *frame, long long sA, int a_lo,
+                         int a_hi, cudaStream_t st);
 void launch_tick(int *d_t, int set, int add, cudaStream_t st);   // *d_t = (set >= 0 ? set : *d_t) + add
 int launches_per_inject(int n_src, int n_air, int t, int nTic, int n_src_rim);
 

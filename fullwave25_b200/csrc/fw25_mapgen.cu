@@ -21,11 +21,15 @@
 // HBM traffic per extended voxel: <= 13 float64 reads of the (13x smaller, mostly L2-resident) user grid + 14 x 4 B
 // written: the kernel is bound by the 56 B/voxel it writes.
 
+#include <climits>
+#include <condition_variable>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -73,9 +77,13 @@ struct MgParams {
   // weight tables [3 ramp kinds][axis length], one per engine axis (B unused in 2D): kind 0 polynomial (d nu1),
   // 1 linear (alpha nu1), 2 cosine (d, alpha nu2)
   const double *wA, *wB, *wC;
-  const double *c, *rho, *beta;
-  const double *relax[10];
-  const double *alpha_coeff, *alpha_power, *lut, *lut_alpha, *lut_power;
+  // user-grid inputs: float64 (the reference's Medium) or float32 (in_f32), planes [u_plane0, ...) of the user grid
+  const void *c, *rho, *beta;
+  const void *relax[10];
+  const void *alpha_coeff, *alpha_power;
+  int in_f32, u_plane0;
+  int a0;                  // first extended plane of this launch (blockIdx.z = 0)
+  const double *lut, *lut_alpha, *lut_power;
   const unsigned char *lut_invalid;
   int lut_na, lut_np;
   double alpha_min, alpha_max, power_min, power_max;
@@ -114,10 +122,14 @@ __device__ __forceinline__ void a_and_b(double d, double kappa, double alpha, do
   b = __double2float_rn(bb);
 }
 
+__device__ __forceinline__ double user(const void *ptr, long long i, int in_f32) {
+  return in_f32 ? (double)__ldg(static_cast<const float *>(ptr) + i) : __ldg(static_cast<const double *>(ptr) + i);
+}
+
 __global__ void __launch_bounds__(256) k_mapgen(const MgParams P) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;   // contiguous axis (incl. the padding columns)
   const int b = blockIdx.y;
-  const int a = blockIdx.z;
+  const int a = blockIdx.z + P.a0;
   if (c >= P.pitch) return;
   const long long o = ((long long)a * P.nB + b) * P.pitch + c;
   if (c >= P.nC) {   // padding: zeros, like the engine's own uploads
@@ -129,12 +141,13 @@ __global__ void __launch_bounds__(256) k_mapgen(const MgParams P) {
   const int ua = min(max(a - P.nb, 0), P.uA - 1);
   const int ub = min(max(b - P.nb, 0), P.uB - 1);
   const int uc = min(max(c - P.nb, 0), P.uC - 1);
-  const long long u = ((long long)ua * P.uB + ub) * P.uC + uc;
+  const long long u = ((long long)(ua - P.u_plane0) * P.uB + ub) * P.uC + uc;
+  const int f32 = P.in_f32;
 
-  const double cs = __ldg(P.c + u), rho = __ldg(P.rho + u);
+  const double cs = user(P.c, u, f32), rho = user(P.rho, u, f32);
   P.out[0][o] = __double2float_rn(rho);
   P.out[1][o] = __double2float_rn(__dmul_rn(__dmul_rn(cs, cs), rho));   // np.multiply(sound_speed**2, density)
-  P.out[2][o] = __double2float_rn(__ldg(P.beta + u));
+  P.out[2][o] = __double2float_rn(user(P.beta, u, f32));
   {
     const long long dense = ((long long)a * P.nB + b) * P.nC + c;
     int dc = (int)rint(__dadd_rn(cs, 1e-9)) - P.c_round_min;   // np.round(c + 1e-9): ties to even, like rint
@@ -145,10 +158,10 @@ __global__ void __launch_bounds__(256) k_mapgen(const MgParams P) {
   double r[10];
   if (P.relax[0]) {
 #pragma unroll
-    for (int i = 0; i < 10; ++i) r[i] = __ldg(P.relax[i] + u);
+    for (int i = 0; i < 10; ++i) r[i] = user(P.relax[i], u, f32);
   } else {
-    const double al = clip(__ldg(P.alpha_coeff + u), P.alpha_min, P.alpha_max);
-    const double pw = clip(__ldg(P.alpha_power + u), P.power_min, P.power_max);
+    const double al = clip(user(P.alpha_coeff, u, f32), P.alpha_min, P.alpha_max);
+    const double pw = clip(user(P.alpha_power, u, f32), P.power_min, P.power_max);
     const int ia = search_left(P.lut_alpha, P.lut_na, al);
     const int ip = search_left(P.lut_power, P.lut_np, pw);
     const long long e = (long long)ia * P.lut_np + ip;
@@ -221,17 +234,26 @@ struct fw25_mapset {
 static const char *const kMapNames[13] = {"rho",    "K",      "beta",   "kappax", "kappau", "apmlx1", "bpmlx1",
                                           "apmlx2", "bpmlx2", "apmlu1", "bpmlu1", "apmlu2", "bpmlu2"};
 
-extern "C" {
+namespace fw25 {
+namespace {
 
-int fw25_mapgen(const fw25_medium *md, int32_t device, fw25_mapset **out, double *stats_ms) {
-  if (!md || !out) { g_err = "fw25_mapgen: NULL argument"; return 1; }
-  *out = nullptr;
-  std::unique_ptr<fw25_mapset> ms(new fw25_mapset());
-  void *scratch = nullptr;   // device scratch: user-grid inputs, tables
-  cudaStream_t st = nullptr;
-  cudaEvent_t ev[3] = {};
-  int rc = 0;
-  try {
+// A validated medium: kernel parameters, the small tables on the device, the output mapset.  The user-grid maps
+// themselves are uploaded by the caller -- all at once (fw25_mapgen) or plane block by plane block (MapStream).
+struct MapgenPlan {
+  MgParams P{};
+  std::unique_ptr<fw25_mapset> ms;
+  void *tables = nullptr;                  // device: weight tables, look-up database, invalid counter
+  int n_user = 0;                          // user-grid maps: c, rho, beta + 10 relaxation maps or alpha_coeff, alpha_power
+  const void *host_user[13] = {};
+  size_t slot_off[13] = {};                // byte offset inside MgParams of each user map's pointer
+  size_t elem = 8;                         // bytes per user-grid value
+  size_t user_plane = 0;                   // values per user-grid x plane
+
+  ~MapgenPlan() {
+    if (tables) cudaFree(tables);
+  }
+
+  void create(const fw25_medium *md, int device, cudaStream_t st) {
     if (md->ndim != 2 && md->ndim != 3) mg_fail("fw25_mapgen: ndim must be 2 or 3");
     const int ndim = md->ndim;
     const int nz_u = ndim == 3 ? md->nz : 1;
@@ -257,11 +279,11 @@ int fw25_mapgen(const fw25_medium *md, int32_t device, fw25_mapset **out, double
     if (ex > INT32_MAX || ey > INT32_MAX || ez > INT32_MAX) mg_fail("fw25_mapgen: extended grid too large");
 
     MG_CUDA(cudaSetDevice(device));
+    ms.reset(new fw25_mapset());
     ms->device = device;
     ms->ndim = ndim; ms->nX = (int)ex; ms->nY = (int)ey; ms->nZ = (int)ez;
     ms->dcmap_full3d = md->dcmap_full3d != 0 || ndim == 2;
 
-    MgParams P{};
     P.ndim = ndim;
     P.nA = (int)ex; P.nB = ndim == 3 ? (int)ey : 1; P.nC = ndim == 3 ? (int)ez : (int)ey;
     P.uA = md->nx; P.uB = ndim == 3 ? md->ny : 1; P.uC = ndim == 3 ? nz_u : md->ny;
@@ -273,23 +295,31 @@ int fw25_mapgen(const fw25_medium *md, int32_t device, fw25_mapset **out, double
     P.dcmap_limit = (ndim == 3 && !md->dcmap_full3d) ? ex * ey : -1;
     P.lut_na = md->lut_na; P.lut_np = md->lut_np;
     P.alpha_min = md->alpha_min; P.alpha_max = md->alpha_max; P.power_min = md->power_min; P.power_max = md->power_max;
+    P.in_f32 = md->input_f32 != 0;
+    elem = P.in_f32 ? 4 : 8;
+    user_plane = (size_t)P.uB * P.uC;
+    if (P.nB > 65535 || P.nA > 65535) mg_fail("fw25_mapgen: more than 65535 rows per axis");
 
-    // One scratch allocation (user-grid inputs, tables) and one output allocation: a handful of driver calls
-    // whatever the number of maps.
-    MG_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    for (auto &e : ev) MG_CUDA(cudaEventCreate(&e));
-    const size_t upts = (size_t)md->nx * md->ny * nz_u;
+    auto user_map = [&](const void *host, const void **slot) {
+      host_user[n_user] = host;
+      slot_off[n_user] = (size_t)(reinterpret_cast<const char *>(slot) - reinterpret_cast<const char *>(&P));
+      ++n_user;
+    };
+    user_map(md->sound_speed, &P.c);
+    user_map(md->density, &P.rho);
+    user_map(md->beta, &P.beta);
+    if (direct) {
+      for (int i = 0; i < 10; ++i) user_map(md->relax[i], &P.relax[i]);
+    } else {
+      user_map(md->alpha_coeff, &P.alpha_coeff);
+      user_map(md->alpha_power, &P.alpha_power);
+    }
+
+    // the small tables: one allocation, copied before anything else on `st`
     struct Item { const void *host; size_t bytes; const void **slot; };
     std::vector<Item> items;
     auto want = [&](const void *host, size_t bytes, const void **slot) { items.push_back({host, bytes, slot}); };
-    want(md->sound_speed, upts * 8, (const void **)&P.c);
-    want(md->density, upts * 8, (const void **)&P.rho);
-    want(md->beta, upts * 8, (const void **)&P.beta);
-    if (direct) {
-      for (int i = 0; i < 10; ++i) want(md->relax[i], upts * 8, (const void **)&P.relax[i]);
-    } else {
-      want(md->alpha_coeff, upts * 8, (const void **)&P.alpha_coeff);
-      want(md->alpha_power, upts * 8, (const void **)&P.alpha_power);
+    if (!direct) {
       want(md->lut, (size_t)md->lut_na * md->lut_np * 10 * 8, (const void **)&P.lut);
       want(md->lut_alpha, (size_t)md->lut_na * 8, (const void **)&P.lut_alpha);
       want(md->lut_power, (size_t)md->lut_np * 8, (const void **)&P.lut_power);
@@ -312,32 +342,223 @@ int fw25_mapgen(const fw25_medium *md, int32_t device, fw25_mapset **out, double
     want(&zero, 8, (const void **)&P.invalid_count);
     size_t total = 0;
     for (auto &it : items) total += (it.bytes + 255) / 256 * 256;
-    MG_CUDA(cudaMalloc(&scratch, total));
-    ms->cells = (size_t)P.nA * P.nB * P.pitch;
-    MG_CUDA(cudaMalloc((void **)&ms->block, ms->cells * 4 * 14));
-    for (int i = 0; i < 13; ++i) P.out[i] = ms->maps[i] = ms->block + (size_t)i * ms->cells;
-    P.dcmap = ms->dcmap = reinterpret_cast<int32_t *>(ms->block + (size_t)13 * ms->cells);
-
-    MG_CUDA(cudaEventRecord(ev[0], st));
+    MG_CUDA(cudaMalloc(&tables, total));
     size_t off = 0;
     for (auto &it : items) {
-      char *d = static_cast<char *>(scratch) + off;
+      char *d = static_cast<char *>(tables) + off;
       MG_CUDA(cudaMemcpyAsync(d, it.host, it.bytes, cudaMemcpyHostToDevice, st));
       *it.slot = d;
       off += (it.bytes + 255) / 256 * 256;
     }
-    unsigned long long *d_inv = P.invalid_count;
+    MG_CUDA(cudaStreamSynchronize(st));             // the host vectors above go out of scope
 
-    if (P.nB > 65535 || P.nA > 65535) mg_fail("fw25_mapgen: more than 65535 rows per axis");
-    MG_CUDA(cudaEventRecord(ev[1], st));
-    dim3 grid((P.pitch + 255) / 256, P.nB, P.nA);
-    k_mapgen<<<grid, 256, 0, st>>>(P);
+    ms->cells = (size_t)P.nA * P.nB * P.pitch;
+    MG_CUDA(cudaMalloc((void **)&ms->block, ms->cells * 4 * 14));
+    for (int i = 0; i < 13; ++i) P.out[i] = ms->maps[i] = ms->block + (size_t)i * ms->cells;
+    P.dcmap = ms->dcmap = reinterpret_cast<int32_t *>(ms->block + (size_t)13 * ms->cells);
+  }
+
+  // extended planes [a_lo, a_hi) from user-grid planes that start at u_plane0 in the buffers `dev_user[i]`
+  void launch(int a_lo, int a_hi, void *const *dev_user, int u_plane0, cudaStream_t st) {
+    if (a_hi <= a_lo) return;
+    MgParams Q = P;
+    for (int i = 0; i < n_user; ++i) *reinterpret_cast<const void **>(reinterpret_cast<char *>(&Q) + slot_off[i]) = dev_user[i];
+    Q.u_plane0 = u_plane0;
+    Q.a0 = a_lo;
+    dim3 grid((Q.pitch + 255) / 256, Q.nB, a_hi - a_lo);
+    k_mapgen<<<grid, 256, 0, st>>>(Q);
     MG_CUDA(cudaGetLastError());
-    MG_CUDA(cudaEventRecord(ev[2], st));
+  }
+
+  // user planes the extended planes [a_lo, a_hi) read: [first, last]
+  void user_range(int a_lo, int a_hi, int &first, int &last) const {
+    first = std::min(std::max(a_lo - P.nb, 0), P.uA - 1);
+    last = std::min(std::max(a_hi - 1 - P.nb, 0), P.uA - 1);
+  }
+
+  long long read_invalid(cudaStream_t st) {
     unsigned long long inv = 0;
-    MG_CUDA(cudaMemcpyAsync(&inv, d_inv, 8, cudaMemcpyDeviceToHost, st));
+    MG_CUDA(cudaMemcpyAsync(&inv, P.invalid_count, 8, cudaMemcpyDeviceToHost, st));
     MG_CUDA(cudaStreamSynchronize(st));
-    ms->invalid = (long long)inv;
+    return (long long)inv;
+  }
+};
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+// MapStream: the maps become valid plane block by plane block, in x order, while the caller already steps.  An
+// uploader thread sends the user-grid planes each block reads (a ring of three slots in HBM, the whole user grid
+// never sits on the device) and launches k_mapgen for the block on its own stream; ready[b] is recorded behind it.
+struct MapStream {
+  MapgenPlan plan;
+  int device = 0, block = 32, n_blocks = 0;
+  cudaStream_t up = nullptr, gen = nullptr;
+  std::vector<cudaEvent_t> ready, landed, slot_free;
+  static constexpr int kSlots = 3;
+  char *ring = nullptr;
+  size_t slot_bytes = 0, map_bytes = 0;   // per slot; per user map inside a slot
+  std::thread th;
+  std::mutex m;
+  std::condition_variable cv;
+  int recorded = 0;                        // events ready[0 .. recorded) have been recorded
+  bool failed = false;
+  std::string err;
+  double upload_ms = 0, kernel_ms = 0;
+  int64_t h2d_bytes = 0;
+  cudaEvent_t t_begin = nullptr, t_end = nullptr;
+
+  ~MapStream() {
+    if (th.joinable()) th.join();
+    cudaSetDevice(device);
+    for (auto &v : {&ready, &landed, &slot_free})
+      for (cudaEvent_t e : *v)
+        if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {t_begin, t_end})
+      if (e) cudaEventDestroy(e);
+    if (up) { cudaStreamSynchronize(up); cudaStreamDestroy(up); }
+    if (gen) { cudaStreamSynchronize(gen); cudaStreamDestroy(gen); }
+    if (ring) cudaFree(ring);
+  }
+
+  void start(const fw25_medium *md, int dev, int block_planes) {
+    device = dev;
+    block = block_planes;
+    MG_CUDA(cudaSetDevice(device));
+    MG_CUDA(cudaStreamCreateWithFlags(&up, cudaStreamNonBlocking));
+    MG_CUDA(cudaStreamCreateWithFlags(&gen, cudaStreamNonBlocking));
+    plan.create(md, device, up);
+    n_blocks = (plan.P.nA + block - 1) / block;
+    map_bytes = (size_t)block * plan.user_plane * plan.elem;
+    map_bytes = (map_bytes + 255) / 256 * 256;
+    slot_bytes = map_bytes * plan.n_user;
+    MG_CUDA(cudaMalloc((void **)&ring, slot_bytes * kSlots));
+    ready.assign(n_blocks, nullptr);
+    landed.assign(n_blocks, nullptr);
+    slot_free.assign(n_blocks, nullptr);
+    for (int b = 0; b < n_blocks; ++b) {
+      MG_CUDA(cudaEventCreateWithFlags(&ready[b], cudaEventDisableTiming));
+      MG_CUDA(cudaEventCreateWithFlags(&landed[b], cudaEventDisableTiming));
+    }
+    MG_CUDA(cudaEventCreate(&t_begin));
+    MG_CUDA(cudaEventCreate(&t_end));
+    th = std::thread([this] { body(); });
+  }
+
+  void body() {
+    try {
+      MG_CUDA(cudaSetDevice(device));
+      MG_CUDA(cudaEventRecord(t_begin, up));
+      for (int b = 0; b < n_blocks; ++b) {
+        const int a_lo = b * block, a_hi = std::min(a_lo + block, plan.P.nA);
+        int u0, u1;
+        plan.user_range(a_lo, a_hi, u0, u1);
+        char *slot = ring + (size_t)(b % kSlots) * slot_bytes;
+        if (b >= kSlots) MG_CUDA(cudaStreamWaitEvent(up, ready[b - kSlots], 0));   // the slot's last reader is done
+        void *dev_user[13];
+        const size_t bytes = (size_t)(u1 - u0 + 1) * plan.user_plane * plan.elem;
+        for (int i = 0; i < plan.n_user; ++i) {
+          dev_user[i] = slot + (size_t)i * map_bytes;
+          MG_CUDA(cudaMemcpyAsync(dev_user[i], static_cast<const char *>(plan.host_user[i]) +
+                                  (size_t)u0 * plan.user_plane * plan.elem, bytes, cudaMemcpyHostToDevice, up));
+        }
+        h2d_bytes += (int64_t)bytes * plan.n_user;
+        MG_CUDA(cudaEventRecord(landed[b], up));
+        MG_CUDA(cudaStreamWaitEvent(gen, landed[b], 0));
+        plan.launch(a_lo, a_hi, dev_user, u0, gen);
+        MG_CUDA(cudaEventRecord(ready[b], gen));
+        {
+          std::lock_guard<std::mutex> lk(m);
+          recorded = b + 1;
+        }
+        cv.notify_all();
+      }
+      MG_CUDA(cudaEventRecord(t_end, up));
+    } catch (const MgFail &) {
+      std::lock_guard<std::mutex> lk(m);
+      failed = true;
+      err = g_err;                                   // (thread-local: hand it to the waiting thread)
+      cv.notify_all();
+    }
+  }
+
+  // blocks until ready[b] has been RECORDED (waiting on an unrecorded event would be a no-op); nullptr on failure
+  cudaEvent_t wait_recorded(int b) {
+    std::unique_lock<std::mutex> lk(m);
+    cv.wait(lk, [&] { return failed || recorded > b; });
+    if (failed) { g_err = err; return nullptr; }
+    return ready[b];
+  }
+
+  void finish(fw25_mapset *ms) {
+    if (th.joinable()) th.join();
+    if (failed) { g_err = err; throw MgFail{2}; }
+    MG_CUDA(cudaSetDevice(device));
+    ms->invalid = plan.read_invalid(gen);
+    MG_CUDA(cudaStreamSynchronize(up));
+    float a = 0;
+    MG_CUDA(cudaEventElapsedTime(&a, t_begin, t_end));
+    upload_ms = a;
+  }
+};
+
+MapStream *mapstream_start(const fw25_medium *md, int device, int block_planes, fw25_mapset **ms_out) {
+  std::unique_ptr<MapStream> S(new MapStream());
+  try {
+    S->start(md, device, block_planes);
+  } catch (const MgFail &) {
+    return nullptr;
+  }
+  *ms_out = S->plan.ms.get();                        // owned by the stream until mapstream_release_mapset
+  return S.release();
+}
+int mapstream_blocks(const MapStream *S) { return S->n_blocks; }
+cudaEvent_t mapstream_wait_recorded(MapStream *S, int b) { return S->wait_recorded(b); }
+fw25_mapset *mapstream_finish(MapStream *S, double *stats_ms, int64_t *h2d_bytes) {
+  fw25_mapset *ms = S->plan.ms.get();
+  try {
+    S->finish(ms);
+  } catch (const MgFail &) {
+    return nullptr;
+  }
+  if (stats_ms) { stats_ms[0] = S->upload_ms; stats_ms[1] = 0; }
+  if (h2d_bytes) *h2d_bytes = S->h2d_bytes;
+  return S->plan.ms.release();
+}
+void mapstream_destroy(MapStream *S) { delete S; }
+
+}  // namespace fw25
+
+extern "C" {
+
+int fw25_mapgen(const fw25_medium *md, int32_t device, fw25_mapset **out, double *stats_ms) {
+  if (!md || !out) { g_err = "fw25_mapgen: NULL argument"; return 1; }
+  *out = nullptr;
+  MapgenPlan plan;
+  void *scratch = nullptr;   // device scratch: the user-grid inputs
+  cudaStream_t st = nullptr;
+  cudaEvent_t ev[3] = {};
+  int rc = 0;
+  try {
+    MG_CUDA(cudaSetDevice(device));
+    MG_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    for (auto &e : ev) MG_CUDA(cudaEventCreate(&e));
+    plan.create(md, device, st);
+    // One scratch allocation for the user-grid inputs and one output allocation: a handful of driver calls whatever
+    // the number of maps.
+    const size_t per = ((size_t)plan.P.uA * plan.user_plane * plan.elem + 255) / 256 * 256;
+    MG_CUDA(cudaMalloc(&scratch, per * plan.n_user));
+    MG_CUDA(cudaEventRecord(ev[0], st));
+    void *dev_user[13];
+    for (int i = 0; i < plan.n_user; ++i) {
+      dev_user[i] = static_cast<char *>(scratch) + (size_t)i * per;
+      MG_CUDA(cudaMemcpyAsync(dev_user[i], plan.host_user[i], (size_t)plan.P.uA * plan.user_plane * plan.elem,
+                              cudaMemcpyHostToDevice, st));
+    }
+    MG_CUDA(cudaEventRecord(ev[1], st));
+    plan.launch(0, plan.P.nA, dev_user, 0, st);
+    MG_CUDA(cudaEventRecord(ev[2], st));
+    plan.ms->invalid = plan.read_invalid(st);
     if (stats_ms) {
       float a = 0, b = 0;
       MG_CUDA(cudaEventElapsedTime(&a, ev[0], ev[1]));
@@ -352,7 +573,7 @@ int fw25_mapgen(const fw25_medium *md, int32_t device, fw25_mapset **out, double
   for (auto &e : ev)
     if (e) cudaEventDestroy(e);
   if (rc) return rc;
-  *out = ms.release();
+  *out = plan.ms.release();
   return 0;
 }
 

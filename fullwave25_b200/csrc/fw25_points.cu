@@ -85,6 +85,40 @@ __global__ void k_record_box(const float *__restrict__ p, float *__restrict__ fr
   frame[((size_t)a * B.wb + b) * B.wc + c] = rim ? 0.0f : p[(long long)la * B.sA + (long long)lb * B.sB + lc];
 }
 
+// Plane-range forms for the time-skewed start (Engine::run_skewed): only the entries whose plane index/sA lies in
+// [a_lo, a_hi) are touched, so that injection and recording can follow the sweeps block by block.
+__global__ void k_inject_range(float *__restrict__ p, const long long *__restrict__ src_idx,
+                               const int *__restrict__ src_row, const unsigned char *__restrict__ src_flag, int n_src,
+                               const float *__restrict__ icmat, int nTic, int t, const long long *__restrict__ air_idx,
+                               int n_air, long long sA, int a_lo, int a_hi) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_src) {
+    const long long s = src_idx[i];
+    const int a = (int)(s / sA);
+    if (a < a_lo || a >= a_hi) return;
+    const unsigned char f = src_flag[i];
+    if (f & 2) return;
+    if (t < nTic) p[s] = icmat[(size_t)src_row[i] * nTic + t];
+    else if (f & 1) p[s] = 0.0f;
+  } else if (i < n_src + n_air) {
+    const long long s = air_idx[i - n_src];
+    const int a = (int)(s / sA);
+    if (a < a_lo || a >= a_hi) return;
+    p[s] = 0.0f;
+  }
+}
+
+__global__ void k_record_range(const float *__restrict__ p, const long long *__restrict__ sens_idx, int n_sens,
+                               float *__restrict__ frame, long long sA, int a_lo, int a_hi) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_sens) return;
+  const long long s = sens_idx[i];
+  if (s < 0) return;                                     // rim sensors read 0: the ring starts out zeroed
+  const int a = (int)(s / sA);
+  if (a < a_lo || a >= a_hi) return;
+  frame[i] = p[s];
+}
+
 __global__ void k_tick(int *d_t, int set, int add) {
   pdl_trigger();
   pdl_wait();
@@ -142,6 +176,20 @@ void launch_record_box(const float *p, float *frames, long long n_sens, const in
   if (n_sens <= 0) return;
   dim3 grid((B.wc + 255) / 256, B.wb, B.wa);
   launch_pdl(k_record_box, grid, dim3(256), 0, st, p, frames, n_sens, d_t, t_off, modT, cap, B);
+}
+
+void launch_inject_range(float *p, const long long *src_idx, const int *src_row, const unsigned char *src_flag, int n_src,
+                         const float *icmat, int nTic, int t, const long long *air_idx, int n_air, long long sA, int a_lo,
+                         int a_hi, cudaStream_t st) {
+  const int n = n_src + n_air;
+  if (n > 0)
+    k_inject_range<<<(n + 255) / 256, 256, 0, st>>>(p, src_idx, src_row, src_flag, n_src, icmat, nTic, t, air_idx, n_air, sA,
+                                                    a_lo, a_hi);
+}
+
+void launch_record_range(const float *p, const long long *sens_idx, int n_sens, float *frame, long long sA, int a_lo,
+                         int a_hi, cudaStream_t st) {
+  if (n_sens > 0) k_record_range<<<(n_sens + 255) / 256, 256, 0, st>>>(p, sens_idx, n_sens, frame, sA, a_lo, a_hi);
 }
 
 void launch_tick(int *d_t, int set, int add, cudaStream_t st) { launch_pdl(k_tick, dim3(1), dim3(1), 0, st, d_t, set, add); }

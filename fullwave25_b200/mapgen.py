@@ -42,6 +42,7 @@ class CMedium(C.Structure):
         ("alpha_min", C.c_double), ("alpha_max", C.c_double), ("power_min", C.c_double), ("power_max", C.c_double),
         ("lut_invalid", C.c_void_p),
         ("c_round_min", C.c_int32), ("dcmap_full3d", C.c_int32),
+        ("input_f32", C.c_int32), ("reserved_", C.c_int32),
     ]
 
 

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define FW25_ABI_VERSION 5
+#define FW25_ABI_VERSION 6
 #define FW25_M 8 /* stencil half-width: solver.py:296 (m_spatial_order = 8), kernels launched with M = 8 */
 
 /* Anisotropic-relaxation file set (upstream `use_isotropic_relaxation=False`, input_file_writer.py:592-620; engine
@@ -202,6 +202,10 @@ typedef struct fw25_medium {
   const uint8_t *lut_invalid;                /* invalid_matrix [lut_na][lut_np] or NULL: counted, like the warning */
   int32_t c_round_min;                       /* round(min(c) + 1e-9): dcmap = round(c + 1e-9) - c_round_min */
   int32_t dcmap_full3d;                      /* as fw25_problem.dcmap_full3d: 0 zeroes dcmap beyond the first nX*nY entries */
+  int32_t input_f32;                         /* 0: the user-grid maps (sound_speed .. alpha_power) are float64, what the
+                                                reference's Medium holds; 1: they are float32 arrays (converted exactly on
+                                                the device; half the host->device traffic).  Tables stay float64. */
+  int32_t reserved_;
 } fw25_medium;
 
 typedef struct fw25_mapset fw25_mapset; /* opaque: the 13 float maps + dcmap, device-resident, engine layout */
@@ -217,6 +221,16 @@ int fw25_mapset_problem(const fw25_mapset *ms, fw25_problem *pb);
 int fw25_mapset_read(const fw25_mapset *ms, const char *name, void *out);
 int64_t fw25_mapset_invalid_count(const fw25_mapset *ms);   /* voxels that hit an invalid look-up entry */
 void fw25_mapset_destroy(fw25_mapset *ms);
+
+/* ---- Whole job from the USER-grid medium in ONE call: what `Solver.run` does between `PMLBuilder.run` and loading
+ * genout.dat (solver.py:693-759) -- fw25_mapgen + fw25_run, pipelined.  The user-grid maps go up plane block by plane
+ * block (x is the slowest axis of the reference's arrays), the coefficient maps of a block are generated as soon as its
+ * planes have landed, and the first time steps already sweep the blocks that are ready -- x-marching sweeps, skewed in
+ * time by two blocks per step -- while the rest of the medium is still on its way over PCIe.  Results are bit-identical
+ * to fw25_mapgen followed by fw25_run.  pb supplies nT, nTic, modT, ndmap, dX, dT, dmap and the coordinate lists (GLOBAL,
+ * extended-grid coordinates); its grid sizes and map pointers are ignored (they follow from md).  One device. */
+int fw25_run_medium(const fw25_medium *md, const fw25_problem *pb, int32_t device, float *genout, size_t genout_len,
+                    fw25_stats *stats);
 
 const char *fw25_last_error(void);
 int32_t fw25_abi_version(void);

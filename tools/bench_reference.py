@@ -92,6 +92,11 @@ def step_times(stamps, W: int, K: int, modT: int):
     return t0, t1, stamps[t1] - stamps[t0]
 
 
+def ref_nT(W: int, K: int, modT: int) -> int:
+    """Steps the reference arm runs (and our arm's same-grid run, so that the frames can be compared by hash)."""
+    return W + K + 2 * modT + 1
+
+
 def choose_planes(world: int, nY: int, nZ: int, forced: int | None = None):
     """Largest per-GPU slab the reference can run here: int32 element counts in its host code (global points < 2^31),
     184 B/point on the device, and host RAM for the .dat files in tmpfs plus the engine's own host copies."""
@@ -100,10 +105,10 @@ def choose_planes(world: int, nY: int, nZ: int, forced: int | None = None):
     if forced:
         return forced, {"forced": True}
     plane = nY * nZ
-    ram = psutil.virtual_memory().available
-    shm = shutil.disk_usage("/dev/shm").free if Path("/dev/shm").exists() else 0
+    ram = psutil.virtual_memory().total         # totals, not what is free right now: both arms must pick the same grid
+    shm = shutil.disk_usage("/dev/shm").total if Path("/dev/shm").exists() else 0
     gpu = torch.cuda.get_device_properties(0).total_memory
-    why = {"host_ram_available_GB": round(ram / 1e9, 1), "dev_shm_free_GB": round(shm / 1e9, 1),
+    why = {"host_ram_GB": round(ram / 1e9, 1), "dev_shm_GB": round(shm / 1e9, 1),
            "gpu_GB": round(gpu / 1e9, 1)}
     for p in PLANES:
         pts = p * world * plane
@@ -127,7 +132,15 @@ def write_inputs(work: Path, gshape, nT: int, medium: dict, device, chunk: int =
     nX, nY, nZ = gshape
     work.mkdir(parents=True, exist_ok=True)
     names = MAP_NAMES + ("dcmap",)
-    files = {n: open(work / f"{n}.dat", "wb") for n in names}
+    fds = {n: os.open(work / f"{n}.dat", os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o644) for n in names}
+    plane_bytes = nY * nZ * 4
+
+    def put(fd, arr, offset):
+        """Positional write: several chunks of one file may be in flight at once, in any order."""
+        buf = memoryview(arr).cast("B")
+        done = 0
+        while done < len(buf):
+            done += os.pwrite(fd, buf[done: done + (1 << 30)], offset + done)
     pool = ThreadPoolExecutor(max_workers=len(names))
     pb0 = None
     stage = [{n: torch.empty((chunk, nY, nZ), dtype=torch.int32 if n == "dcmap" else torch.float32, pin_memory=True)
@@ -146,13 +159,13 @@ def write_inputs(work: Path, gshape, nT: int, medium: dict, device, chunk: int =
             st[n][: x1 - x0].copy_(maps[n][..., :nZ], non_blocking=True)
         torch.cuda.synchronize()
         del maps
-        futs.append([pool.submit(st[n].numpy()[: x1 - x0].tofile, files[n]) for n in names])
+        futs.append([pool.submit(put, fds[n], st[n].numpy()[: x1 - x0], x0 * plane_bytes) for n in names])
     for fs in futs:
         for f in fs:
             f.result()
     pool.shutdown()
-    for f in files.values():
-        f.close()
+    for fd in fds.values():
+        os.close(fd)
     del stage
     torch.cuda.empty_cache()
     pb = pb0
@@ -204,7 +217,7 @@ def run_reference(args, *, metric: str, unit: str, workload: str, medium: dict) 
     if planes is None:
         return unavailable(f"no grid of the workload fits this box for the reference engine: {why}")
     modT = medium["modT"]
-    nT = W + K + 2 * modT + 1
+    nT = ref_nT(W, K, modT)
     dev = torch.device("cuda", 0)
     work = Path("/dev/shm" if Path("/dev/shm").exists() else tempfile.gettempdir()) / "fw25_bench_ref"
     tried = []
