@@ -363,7 +363,15 @@ def run_ours(args):
     # ---- (5) end to end through the public API from HOST buffers
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(args, rank, world, dev, comm, (main, bnd), pb_full, maps_full, frames_resident, barrier, max_over_ranks)
+        holder = [maps_full]                                # hand the device maps over: run_e2e must be able to free them
+        maps_full = None
+        hostmaps = run_e2e(args, rank, world, dev, comm, (main, bnd), pb_full, holder, frames_resident, barrier, max_over_ranks)
+        if world == 1:
+            free_device()
+            e2e = run_e2e_medium(args, dev)
+            e2e["hostmaps_variant"] = hostmaps
+        else:
+            e2e = hostmaps
 
     if rank == 0:
         config["same_grid"] = same
@@ -408,8 +416,78 @@ def traffic_from_profile(kernel: str, grid) -> dict:
     return {}
 
 
-def run_e2e(args, rank, world, dev, comm, streams, pb, maps, frames_chk, barrier, max_over_ranks):
+def run_e2e_medium(args, dev, max_mismatch_report: int = 4):
+    """N = 1: the whole job through the plugin call a `fullwave.Solver.run` replacement makes -- `fw25_run_medium`
+    (include/fw25.h) -- from the USER-grid medium in pinned HOST memory: sound_speed, density, beta, alpha_coeff,
+    alpha_power (float32, what a `fullwave.Medium` holds on the user grid) + the relaxation look-up table.  Inside the
+    timed region: device allocation, the host->device copies of the medium (block by block), map generation, all K
+    steps (the first ones time-skewed under the upload), the sensor frames back on the host, and freeing the device."""
+    import torch
+    from fullwave25_b200 import engine, lut_standin, mapgen, synthetic_device
+    from fullwave25_b200.problem import MAP_NAMES, Problem
+    nX, nY, nZ = args.grid
+    K = args.steps
+    nb = 8 + MEDIUM["n_pml"] + MEDIUM["n_trans"]
+    user = (nX - 2 * nb, nY - 2 * nb, nZ - 2 * nb)
+    f0, c0, ppw, cfl = 1e6, 1540.0, 12, 0.2
+    dx = c0 / f0 / ppw
+    dt = cfl * dx / c0
+    t_gen = time.perf_counter()
+    um, c_min, c_max, pinned = synthetic_device.make_user_medium(user, device=dev, block=MEDIUM["block"], seed=MEDIUM["seed"])
+    t_gen = time.perf_counter() - t_gen
+    spec = mapgen.MediumSpec(user_shape=user, dt=dt, dx=dx, c0=c0, cfl=cfl, sound_speed=um["sound_speed"],
+                             density=um["density"], beta=um["beta"], alpha_coeff=um["alpha_coeff"],
+                             alpha_power=um["alpha_power"], lut=lut_standin.lookup_table(),
+                             n_pml_layer=MEDIUM["n_pml"], n_transition_layer=MEDIUM["n_trans"], dcmap_full3d=True,
+                             extra={"c_min": c_min, "c_max": c_max})
+    _, dmap, ndmap, _ = spec.stencil_tables()
+    nTic = min(K, int(np.ceil(2.0 / f0 / dt)) + 1)
+    icc, icmat, outc, icczero = synthetic_device._lists(nX, nY, nZ, nb, nTic, dt, dx, f0=f0, c0=c0, seed=MEDIUM["seed"],
+                                                        n_sensors=MEDIUM["n_sensors"], n_air=MEDIUM["n_air"],
+                                                        source_layers=3, amp=1e5)
+    icm = torch.empty(icmat.shape, dtype=torch.float32, pin_memory=True)        # the source signals are inputs too
+    icm.numpy()[...] = icmat
+    none = {name: None for name in MAP_NAMES}
+    pb = Problem(ndim=3, nX=nX, nY=nY, nZ=nZ, nT=K, nTic=nTic, modT=MEDIUM["modT"], ndmap=ndmap,
+                 dX=float(np.float32(dx)), dT=float(np.float32(dt)), **none, dmap=dmap, dcmap=None, icc=icc,
+                 icmat=icm.numpy(), outc=outc, icczero=icczero, extra={}, dcmap_full3d=True)
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    t0 = time.perf_counter()
+    out, st = mapgen.run_medium(spec, pb, device=dev.index or 0)
+    dt_e2e = time.perf_counter() - t0
+    pts = nX * nY * nZ
+    e2e = {"value": pts * K / dt_e2e / 1e9, "unit": UNIT, "h2d_bytes_per_step": st["h2d_bytes"] / K,
+           "d2h_bytes_per_step": st["d2h_bytes"] / K, "seconds": dt_e2e,
+           "api": "fw25_run_medium (C-ABI, include/fw25.h) via fullwave25_b200.mapgen.run_medium: user-grid medium in "
+                  "pinned host memory -> sensor frames on the host",
+           "grid_per_gpu": f"{nX}x{nY}x{nZ}", "user_grid": "x".join(map(str, user)), "input_dtype": "float32",
+           "launches": int(st["kernel_launches"]), "skewed_steps": int(st["skewed_steps"]),
+           "engine_setup_ms": st["setup_ms"], "device_loop_ms": st["loop_ms"], "frames_d2h_ms": st["d2h_ms"],
+           "host_marshal_ms": st["host_marshal_ms"], "native_call_ms": st["native_call_ms"],
+           "medium_generation_s_untimed": round(t_gen, 2), "finite": bool(np.isfinite(out).all()),
+           "absmax": float(np.abs(out).max()) if out.size else None,
+           "relaxation_table": "stand-in (fullwave25_b200/lut_standin.py): the reference's database blob is missing "
+                               "from its checkout",
+           "note": "min / max of the sound speed (the stencil-table range) are properties of the synthetic medium and "
+                   "are passed in; everything else a Solver.run replacement does is inside the timed region"}
+    # parity at full size: the sequential path (one-shot fw25_mapgen, then whole-grid steps) on the same inputs
+    if not args.no_e2e_check:
+        with mapgen.MapSet(spec, device=dev.index or 0) as ms:
+            eng = engine.Engine(pb, device=dev.index or 0, device_maps=ms.device_maps())
+            try:
+                want, _ = eng.run()
+            finally:
+                eng.close()
+        e2e["frames_identical_to_sequential_run"] = bool(np.array_equal(out, want))
+        e2e["nonzero_frame_values"] = int((want != 0).sum())
+    del pinned
+    return e2e
+
+
+def run_e2e(args, rank, world, dev, comm, streams, pb, maps_holder, frames_chk, barrier, max_over_ranks):
     """The same job through the public API with HOST buffers: pinned host maps -> upload -> K steps -> frames."""
+    maps = maps_holder.pop()
     import dataclasses
 
     import psutil
@@ -484,6 +562,7 @@ def main():
                     help="x planes per GPU of the reference arm's grid (default: the largest the reference can hold here)")
     ap.add_argument("--no-ref-crosscheck", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-e2e-check", action="store_true")
     ap.add_argument("--no-strong", action="store_true")
     ap.add_argument("--no-same-grid", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")

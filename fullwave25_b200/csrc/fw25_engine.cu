@@ -78,37 +78,66 @@ void Engine::release_staging() {
 
 void Engine::setup_sources(int ncoords, const int32_t *icc, const float *icmat) {
   const int nd = ndim;
+  FW_CUDA(cudaStreamSynchronize(stream));            // the previous lists may still be in flight (reset)
   for (void *p : src_owned) cudaFree(p);
   src_owned.clear();
   n_src = n_src_rim = 0;
-  std::vector<long long> idx; std::vector<int> row; std::vector<unsigned char> flag;
+  plane_src.assign((size_t)nXl, 0);
   if (ncoords > 0 && (!icc || (!icmat && nTic > 0))) fail(1, "icc / icmat pointer is NULL");
-  for (int i = 0; i < ncoords; ++i) {
-    const int32_t *c = icc + (size_t)i * nd;
-    if (!coord_ok(c)) fail(1, "icc: source coordinate outside the grid");
-    if (c[0] < gx0 || c[0] >= gx0 + nXl) continue;
-    const long long li = lin(c[0], c[1], nd == 3 ? c[2] : 0);
-    idx.push_back(li);
-    row.push_back(i);
-    const bool r = is_rim(c[0], c[1], nd == 3 ? c[2] : M);
-    const bool dead = air_set.count(li) != 0;
-    flag.push_back((unsigned char)((r ? 1 : 0) | (dead ? 2 : 0)));
-    n_src_rim += (r && !dead);
+  // A plane source of a full-size 3D grid is millions of coordinates: the list is resolved by a few threads, each
+  // over a contiguous range of rows, and concatenated in row order.
+  struct Part {
+    std::vector<long long> idx; std::vector<int> row; std::vector<unsigned char> flag, plane;
+    int rim = 0; bool bad = false;
+  };
+  const int n_thr = ncoords >= (1 << 17) ? (int)std::min<unsigned>(8, std::max(1u, std::thread::hardware_concurrency())) : 1;
+  std::vector<Part> parts(n_thr);
+  auto work = [&](int k) {
+    Part &P = parts[k];
+    const int i0 = (int)((long long)ncoords * k / n_thr), i1 = (int)((long long)ncoords * (k + 1) / n_thr);
+    P.plane.assign((size_t)nXl, 0);
+    P.idx.reserve(i1 - i0); P.row.reserve(i1 - i0); P.flag.reserve(i1 - i0);
+    for (int i = i0; i < i1; ++i) {
+      const int32_t *c = icc + (size_t)i * nd;
+      if (!coord_ok(c)) { P.bad = true; return; }
+      if (c[0] < gx0 || c[0] >= gx0 + nXl) continue;
+      const long long li = lin(c[0], c[1], nd == 3 ? c[2] : 0);
+      P.idx.push_back(li);
+      P.row.push_back(i);
+      const bool r = is_rim(c[0], c[1], nd == 3 ? c[2] : M);
+      const bool dead = plane_air[c[0] - gx0] && air_set.count(li) != 0;
+      P.flag.push_back((unsigned char)((r ? 1 : 0) | (dead ? 2 : 0)));
+      P.rim += (r && !dead);
+      if (!dead) P.plane[c[0] - gx0] = 1;
+    }
+  };
+  {
+    std::vector<std::thread> th;
+    for (int k = 1; k < n_thr; ++k) th.emplace_back(work, k);
+    work(0);
+    for (auto &t_ : th) t_.join();
   }
-  n_src = (int)idx.size();
-  if (ndim == 2) { h_src_idx = idx; h_src_row = row; h_src_flag = flag; }
+  h_src_idx.clear(); h_src_row.clear(); h_src_flag.clear();
+  for (Part &P : parts) {
+    if (P.bad) fail(1, "icc: source coordinate outside the grid");
+    h_src_idx.insert(h_src_idx.end(), P.idx.begin(), P.idx.end());
+    h_src_row.insert(h_src_row.end(), P.row.begin(), P.row.end());
+    h_src_flag.insert(h_src_flag.end(), P.flag.begin(), P.flag.end());
+    n_src_rim += P.rim;
+    for (int a = 0; a < nXl; ++a) plane_src[a] |= P.plane[a];
+  }
+  n_src = (int)h_src_idx.size();
   d_src_idx = salloc<long long>(n_src); d_src_row = salloc<int>(n_src); d_src_rim = salloc<unsigned char>(n_src);
   d_icmat = nullptr;
-  if (n_src) {
-    FW_CUDA(cudaMemcpyAsync(d_src_idx, idx.data(), n_src * sizeof(long long), cudaMemcpyHostToDevice, stream));
-    FW_CUDA(cudaMemcpyAsync(d_src_row, row.data(), n_src * sizeof(int), cudaMemcpyHostToDevice, stream));
-    FW_CUDA(cudaMemcpyAsync(d_src_rim, flag.data(), n_src, cudaMemcpyHostToDevice, stream));
+  if (n_src) {   // the host lists are members: nothing here waits for the copies
+    FW_CUDA(cudaMemcpyAsync(d_src_idx, h_src_idx.data(), n_src * sizeof(long long), cudaMemcpyHostToDevice, stream));
+    FW_CUDA(cudaMemcpyAsync(d_src_row, h_src_row.data(), n_src * sizeof(int), cudaMemcpyHostToDevice, stream));
+    FW_CUDA(cudaMemcpyAsync(d_src_rim, h_src_flag.data(), n_src, cudaMemcpyHostToDevice, stream));
     const size_t nic = (size_t)ncoords * nTic;
     d_icmat = salloc<float>(nic);
     if (nic) FW_CUDA(cudaMemcpyAsync(d_icmat, icmat, nic * 4, cudaMemcpyHostToDevice, stream));
     h2d_bytes += (int64_t)nic * 4;
   }
-  FW_CUDA(cudaStreamSynchronize(stream));  // host vectors go out of scope
 }
 
 void Engine::reset(int nT_, int nTic_, int ncoords, const int32_t *icc, const float *icmat) {
@@ -259,9 +288,8 @@ void Engine::init(const fw25_problem &pb, const fw25_slab *slab, int dev) {
     F.dmap = d;
   }
   const bool trace = getenv("FW25_SETUP_TRACE") != nullptr;
-  auto trace_point = [&](const char *what) {
+  auto trace_point = [&](const char *what) {   // host clock only: no synchronisation, the trace must not change the run
     if (!trace) return;
-    cudaStreamSynchronize(stream);
     fprintf(stderr, "[fw25 setup] %-28s t = %8.1f ms   (cudaMalloc so far %.1f ms, h2d %.2f GB)\n", what,
             std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tr0).count() , malloc_ms,
             h2d_bytes / 1e9);
@@ -308,6 +336,8 @@ void Engine::init(const fw25_problem &pb, const fw25_slab *slab, int dev) {
 
   // ---- coordinate lists -> linear indices (bit-exact integer maps)
   const int nd = ndim;
+  plane_air.assign((size_t)nXl, 0);
+  plane_sens.assign((size_t)nXl, 0);
   {  // air voxels (ghost planes included)
     std::vector<long long> idx;
     if (pb.ncoordszero > 0 && !pb.icczero) fail(1, "icczero pointer is NULL");
@@ -316,15 +346,17 @@ void Engine::init(const fw25_problem &pb, const fw25_slab *slab, int dev) {
       if (!coord_ok(c)) fail(1, "icczero: air coordinate outside the grid");
       if (c[0] < gx0 || c[0] >= gx0 + nXl) continue;
       idx.push_back(lin(c[0], c[1], nd == 3 ? c[2] : 0));
+      plane_air[c[0] - gx0] = 1;
     }
     n_air = (int)idx.size();
-    if (ndim == 2) h_air_idx = idx;
+    h_air_idx = idx;                         // (a member: the copy below need not be waited for)
     d_air_idx = dalloc<long long>(n_air);
-    if (n_air) FW_CUDA(cudaMemcpyAsync(d_air_idx, idx.data(), n_air * sizeof(long long), cudaMemcpyHostToDevice, stream));
-    FW_CUDA(cudaStreamSynchronize(stream));
+    if (n_air) FW_CUDA(cudaMemcpyAsync(d_air_idx, h_air_idx.data(), n_air * sizeof(long long), cudaMemcpyHostToDevice, stream));
     air_set.insert(idx.begin(), idx.end());
   }
+  trace_point("state, plans, air list");
   setup_sources(pb.ncoords, pb.icc, pb.icmat);
+  trace_point("source list");
   int32_t found_box[6];
   const int32_t *obox = pb.out_box;
   if (!obox && pb.outc && pb.ncoordsout >= 4096 && detect_box(pb.outc, pb.ncoordsout, nd, found_box)) obox = found_box;
@@ -360,12 +392,12 @@ void Engine::init(const fw25_problem &pb, const fw25_slab *slab, int dev) {
       if (c[0] < own_lo || c[0] >= own_hi) continue;
       sens_ids.push_back(i);
       idx.push_back(is_rim(c[0], c[1], nd == 3 ? c[2] : M) ? -1 : lin(c[0], c[1], nd == 3 ? c[2] : 0));
+      if (idx.back() >= 0) plane_sens[c[0] - gx0] = 1;
     }
     n_sens = (int)idx.size();
-    if (ndim == 2) h_sens_idx = idx;
+    h_sens_idx = idx;
     d_sens_idx = dalloc<long long>(n_sens);
-    if (n_sens) FW_CUDA(cudaMemcpyAsync(d_sens_idx, idx.data(), n_sens * sizeof(long long), cudaMemcpyHostToDevice, stream));
-    FW_CUDA(cudaStreamSynchronize(stream));
+    if (n_sens) FW_CUDA(cudaMemcpyAsync(d_sens_idx, h_sens_idx.data(), n_sens * sizeof(long long), cudaMemcpyHostToDevice, stream));
   }
   n_sens_global = pb.ncoordsout;
   n_frames = nT > 0 ? (nT + modT - 1) / modT : 0;

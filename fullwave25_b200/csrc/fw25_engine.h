@@ -8,8 +8,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <unordered_set>
 #include <vector>
 
@@ -79,6 +81,7 @@ struct Engine {
   int sens_first = 0;                        // box sensors: global outc row of local sensor 0 (rows are contiguous)
   std::vector<void *> src_owned;             // source-list allocations (replaced by reset())
   std::unordered_set<long long> air_set;     // linear indices of the air voxels held locally
+  std::vector<unsigned char> plane_src, plane_air, plane_sens;   // per local plane: holds a live source / air voxel / sensor
   float *d_frames = nullptr;
   int frames_cap = 0, n_frames = 0;
 
@@ -205,6 +208,11 @@ struct Engine {
 
   void init(const fw25_problem &pb, const fw25_slab *slab, int dev);
 
+  // Time-skewed start (fw25_pipeline.cu): steps [0, Ts) over blocks of `block` planes as their maps become valid.
+  // avail(b) blocks until the event behind which block b's maps are valid has been recorded and returns it.
+  bool skew_supported(int Ts) const;
+  void run_skewed(int Ts, int block, const std::function<cudaEvent_t(int)> &avail);
+
   // Per-tile lists of the special cells of the fused 2D step (fw25_internal.h, Fuse2D).  Whole-grid 2D engines
   // only; a source inside the never-updated rim keeps the separate injection kernel.  Opt-in (FW25_FUSE2D=1):
   // measured on a B200 the fused step launches 2.1 kernels per step instead of 3.2-3.6 but is no faster (14.9 vs
@@ -324,5 +332,7 @@ int run_single(const fw25_problem *pb, int dev0, float *genout, fw25_stats *stat
 int run_multi(const fw25_problem *pb, const int32_t *device_ids, int n, float *genout, fw25_stats *stats);
 // the time loop over an existing engine, from its current step to nT (fw25_run_engine)
 void run_loop(Engine &e, float *genout, fw25_stats *stats, double setup_ms);
+// fw25_mapgen + fw25_run pipelined (fw25_pipeline.cu)
+int run_medium(const fw25_medium *md, const fw25_problem *pb, int device, float *genout, fw25_stats *stats);
 
 }  // namespace fw25

@@ -96,7 +96,8 @@ struct MapStream;
 struct fw25_medium;
 struct fw25_mapset;
 namespace fw25 {
-MapStream *mapstream_start(const fw25_medium *md, int device, int block_planes, fw25_mapset **ms_out);
+MapStream *mapstream_start(const fw25_medium *md, int device, int block_planes, fw25_mapset **ms_out);   // allocates
+void mapstream_go(MapStream *S);                                                                          // starts the uploads
 int mapstream_blocks(const MapStream *S);
 cudaEvent_t mapstream_wait_recorded(MapStream *S, int block);
 fw25_mapset *mapstream_finish(MapStream *S, double *stats_ms, int64_t *h2d_bytes);

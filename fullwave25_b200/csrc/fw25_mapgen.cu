@@ -426,7 +426,10 @@ struct MapStream {
     block = block_planes;
     MG_CUDA(cudaSetDevice(device));
     MG_CUDA(cudaStreamCreateWithFlags(&up, cudaStreamNonBlocking));
-    MG_CUDA(cudaStreamCreateWithFlags(&gen, cudaStreamNonBlocking));
+    // the generator kernel shares the GPU with the sweeps of blocks that are already valid: its CTAs go first
+    int lo_pri = 0, hi_pri = 0;
+    MG_CUDA(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
+    MG_CUDA(cudaStreamCreateWithPriority(&gen, cudaStreamNonBlocking, hi_pri));
     plan.create(md, device, up);
     n_blocks = (plan.P.nA + block - 1) / block;
     map_bytes = (size_t)block * plan.user_plane * plan.elem;
@@ -442,8 +445,8 @@ struct MapStream {
     }
     MG_CUDA(cudaEventCreate(&t_begin));
     MG_CUDA(cudaEventCreate(&t_end));
-    th = std::thread([this] { body(); });
   }
+  void go() { th = std::thread([this] { body(); }); }
 
   void body() {
     try {
@@ -454,6 +457,9 @@ struct MapStream {
         int u0, u1;
         plan.user_range(a_lo, a_hi, u0, u1);
         char *slot = ring + (size_t)(b % kSlots) * slot_bytes;
+        // At most three blocks of copies are queued ahead: the copy engine serves its queue in order, and other
+        // host->device traffic of the process must not wait behind the whole medium.
+        if (b >= 3) MG_CUDA(cudaEventSynchronize(landed[b - 3]));
         if (b >= kSlots) MG_CUDA(cudaStreamWaitEvent(up, ready[b - kSlots], 0));   // the slot's last reader is done
         void *dev_user[13];
         const size_t bytes = (size_t)(u1 - u0 + 1) * plan.user_plane * plan.elem;
@@ -512,6 +518,7 @@ MapStream *mapstream_start(const fw25_medium *md, int device, int block_planes, 
   *ms_out = S->plan.ms.get();                        // owned by the stream until mapstream_release_mapset
   return S.release();
 }
+void mapstream_go(MapStream *S) { S->go(); }
 int mapstream_blocks(const MapStream *S) { return S->n_blocks; }
 cudaEvent_t mapstream_wait_recorded(MapStream *S, int b) { return S->wait_recorded(b); }
 fw25_mapset *mapstream_finish(MapStream *S, double *stats_ms, int64_t *h2d_bytes) {

@@ -1,0 +1,169 @@
+// fw25_pipeline.cu -- the first time steps run WHILE the medium is still arriving (fw25_run_medium).
+//
+// Upstream `Solver.run` is strictly sequential: build the maps on the host (`PMLBuilder.run`), write ~20 files, start
+// the binary, which reads and uploads everything and only then steps (solver.py:693-759).  Here the
+// user-grid medium goes to the GPU plane block by plane block -- x is the slowest axis of the reference's arrays, so a
+// block of planes is one contiguous piece of every map -- `k_mapgen` turns each block into the engine's 14 maps as it
+// lands (MapStream, fw25_mapgen.cu), and the x-marching sweeps start on the blocks that are ready.
+//
+// Time skew.  fd_u(t) at plane x reads p_t at x-7 .. x+8, fd_p(t) reads u_{t+1} at x-8 .. x+7 (and v, w at x +- 1), and
+// both update in place.  With blocks of B >= 16 planes, step t may therefore run one block behind its own fd_u and
+// two blocks behind step t-1:
+//
+//     stage k:   for t = 0, 1, 2, ...   m = k - 2 t
+//                  inject(t)  on block m+1      (p_t there is final: fd_p(t-1) passed it earlier in this stage)
+//                  fd_u(t)    on block m        (reads p_t up to 8 planes into block m+1, 7 planes into block m-1)
+//                  fd_p(t)    on block m-1      (reads u_{t+1} of blocks m-2 .. m; block m-2 is overwritten by
+//                  record(t)  on block m-1       fd_u(t+1) only later in this stage)
+//
+// Stage k touches maps of blocks <= k only, so it can be queued as soon as block k has been generated; everything runs
+// on ONE stream in this order, which is what makes the in-place update safe.  Every cell sees exactly the operations,
+// in the order, of whole-grid sweeps -- the kernels are the same, launched over plane ranges -- so the result is
+// bit-identical to the sequential path (tests/test_pipeline.py).
+#include <memory>
+
+#include "fw25_engine.h"
+
+namespace fw25 {
+
+bool Engine::skew_supported(int Ts) const {
+  // listed sensors whose frames all fit the ring (no read-out in the middle of a skewed phase), whole-grid engine,
+  // plane-range sweeps (the warp-specialised 3D kernels or the simple ones), no graph replay
+  const int frames = Ts > 0 ? (Ts + modT - 1) / modT : 0;
+  return ndim == 3 && !sens_box && frames <= frames_cap && own_lo == 0 && own_hi == nX_global && !graph_enabled() &&
+         Ts > 0;
+}
+
+void Engine::run_skewed(int Ts, int block, const std::function<cudaEvent_t(int)> &avail) {
+  if (block < 2 * M) fail(1, "run_skewed: blocks must hold at least 16 planes");
+  if (t != 0) fail(1, "run_skewed: the engine has already stepped");
+  const int NB = (G.nA + block - 1) / block;
+  auto lo = [&](int b) { return b * block; };                       // local planes of block b
+  auto hi = [&](int b) { return std::min((b + 1) * block, G.nA); };
+  auto any = [&](const std::vector<unsigned char> &flag, int b) {
+    for (int a = lo(b); a < hi(b); ++a)
+      if (flag[a]) return true;
+    return false;
+  };
+  auto inject_block = [&](int tt, int b) {
+    const bool src = n_src > 0 && (tt < nTic || n_src_rim > 0) && any(plane_src, b);
+    const bool air = n_air > 0 && any(plane_air, b);
+    if (!src && !air) return;
+    launch_inject_range(F.p, d_src_idx, d_src_row, d_src_rim, src ? n_src : 0, d_icmat, nTic, tt, d_air_idx,
+                        air ? n_air : 0, G.sA, lo(b), hi(b), stream);
+    ++launches;
+  };
+  for (int k = 0; k <= NB + 2 * (Ts - 1); ++k) {
+    if (k < NB) {
+      cudaEvent_t ev = avail(k);
+      if (!ev) throw Fail{2};
+      FW_CUDA(cudaStreamWaitEvent(stream, ev, 0));
+    }
+    for (int tt = 0; tt < Ts; ++tt) {
+      const int m = k - 2 * tt;
+      if (m < -1) break;
+      if (m > NB) continue;                                         // step tt is complete
+      if (m == 0 && tt == 0) inject_block(0, 0);
+      if (m + 1 < NB) inject_block(tt, m + 1);
+      if (m >= 0 && m < NB) sweep_u(gx0 + lo(m), gx0 + hi(m), stream);
+      if (m >= 1 && m - 1 < NB) {
+        sweep_p(gx0 + lo(m - 1), gx0 + hi(m - 1), stream);
+        if (tt % modT == 0 && n_sens > 0 && any(plane_sens, m - 1)) {
+          launch_record_range(F.p, d_sens_idx, n_sens, d_frames + (size_t)((tt / modT) % frames_cap) * n_sens, G.sA,
+                              lo(m - 1), hi(m - 1), stream);
+          ++launches;
+        }
+      }
+    }
+  }
+  FW_CUDA(cudaGetLastError());
+  t = Ts;
+}
+
+// fw25_mapgen + fw25_run in one pipelined call (include/fw25.h, fw25_run_medium)
+int run_medium(const fw25_medium *md, const fw25_problem *pb_in, int device, float *genout, fw25_stats *stats) {
+  using clk = std::chrono::steady_clock;
+  const auto t0 = clk::now();
+  auto ms_since = [&](clk::time_point a) { return std::chrono::duration<double, std::milli>(clk::now() - a).count(); };
+  constexpr int kBlock = 32;                 // one x-marching chunk of the warp-specialised sweeps
+  const bool trace = getenv("FW25_SETUP_TRACE") != nullptr;
+  auto tp = [&](const char *what) {
+    if (trace) fprintf(stderr, "[fw25 run_medium] %-34s t = %8.1f ms\n", what, ms_since(t0));
+  };
+  struct Holder {
+    MapStream *S = nullptr;
+    fw25_engine *h = nullptr;
+    fw25_mapset *ms = nullptr;               // set once ownership has passed from the stream to this call
+    std::function<void(const char *)> tp;
+    ~Holder() {
+      if (h) fw25_destroy(h);
+      if (tp) tp("engine destroyed");
+      if (S) mapstream_destroy(S);
+      if (ms) fw25_mapset_destroy(ms);
+      if (tp) tp("maps freed");
+    }
+  } H;
+  H.tp = tp;
+  fw25_mapset *ms_view = nullptr;
+  H.S = mapstream_start(md, device, kBlock, &ms_view);
+  if (!H.S) return 2;
+  tp("map set allocated");
+  fw25_problem pb = *pb_in;
+  if (fw25_mapset_problem(ms_view, &pb) != 0) return 1;
+  {
+    const int rc = fw25_create(&pb, nullptr, device, &H.h);     // adopts the (still empty) maps; uploads lists, builds plans
+    if (rc) return rc;
+  }
+  Engine &e = H.h->e;
+  // The medium starts to flow only now: the engine's own uploads (coordinate lists from pageable memory, source
+  // signals) would otherwise queue chunk by chunk behind the medium's copies on the one host->device copy engine
+  // (measured: 260 ms instead of 20).
+  FW_CUDA(cudaStreamSynchronize(e.stream));
+  mapstream_go(H.S);
+  tp("engine created, uploads started");
+  const double setup_ms = ms_since(t0);
+  const int NB = mapstream_blocks(H.S);
+  // steps that can start before the last block has arrived; the rest run as whole-grid sweeps
+  int Ts = std::min(e.nT, (NB + 1) / 2);
+  if (const char *ev = getenv("FW25_SKEW_STEPS")) Ts = std::min(e.nT, std::max(0, atoi(ev)));   // tests / A-B runs
+  const int64_t l0 = e.launches;
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+  FW_CUDA(cudaEventCreate(&ev_a));
+  FW_CUDA(cudaEventCreate(&ev_b));
+  FW_CUDA(cudaEventRecord(ev_a, e.stream));
+  if (e.skew_supported(Ts)) {
+    e.run_skewed(Ts, kBlock, [&](int b) { return mapstream_wait_recorded(H.S, b); });
+  } else {                                   // whole-grid stepping needs every block
+    cudaEvent_t last = mapstream_wait_recorded(H.S, NB - 1);
+    if (!last) return 2;
+    FW_CUDA(cudaStreamWaitEvent(e.stream, last, 0));
+    Ts = 0;
+  }
+  FW_CUDA(cudaEventRecord(ev_b, e.stream));
+  tp("skewed steps queued");
+  fw25_stats st{};
+  run_loop(e, genout, &st, 0.0);                              // remaining steps + frames to the host
+  tp("loop done, frames on the host");
+  double gen_ms[2] = {0, 0};
+  int64_t h2d = 0;
+  H.ms = mapstream_finish(H.S, gen_ms, &h2d);                 // joins the uploader; reports a failed upload
+  if (!H.ms) return 2;
+  tp("map stream finished");
+  float skew_ms = 0;
+  FW_CUDA(cudaEventElapsedTime(&skew_ms, ev_a, ev_b));
+  cudaEventDestroy(ev_a);
+  cudaEventDestroy(ev_b);
+  if (stats) {
+    *stats = st;
+    stats->setup_ms = setup_ms;
+    stats->loop_ms = st.loop_ms + skew_ms;
+    stats->kernel_launches = e.launches - l0;
+    stats->h2d_bytes = e.h2d_bytes + h2d;
+    stats->point_updates = (int64_t)e.nXl * e.nY * e.nZ * (int64_t)e.nT;
+    stats->n_devices = 1;
+    stats->skewed_steps = Ts;                                    // steps run time-skewed under the upload
+  }
+  return 0;
+}
+
+}  // namespace fw25

@@ -58,7 +58,7 @@ class CStats(C.Structure):
     _fields_ = [("setup_ms", C.c_double), ("loop_ms", C.c_double), ("d2h_ms", C.c_double),
                 ("kernel_launches", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
                 ("point_updates", C.c_int64), ("halo_bytes", C.c_int64), ("n_devices", C.c_int32),
-                ("reserved_", C.c_int32)]
+                ("skewed_steps", C.c_int32)]
 
 
 _lib = None

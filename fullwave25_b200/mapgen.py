@@ -52,6 +52,8 @@ SIGS = {
     "fw25_mapset_read": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p]),
     "fw25_mapset_invalid_count": (C.c_int64, [C.c_void_p]),
     "fw25_mapset_destroy": (None, [C.c_void_p]),
+    "fw25_run_medium": (C.c_int, [C.POINTER(CMedium), C.POINTER(engine.CProblem), C.c_int32, engine._F, C.c_size_t,
+                                  C.POINTER(engine.CStats)]),
 }
 
 
@@ -125,7 +127,10 @@ class MediumSpec:
         """d, dmap, ndmap and round(min c) from the USER grid: padding by edge replication leaves min / max of
         the sound speed unchanged (input_file_writer.py:95-103, :183-559)."""
         c = self.sound_speed
-        c_min, c_max = c.min(), c.max()
+        if "c_min" in self.extra and "c_max" in self.extra:      # known to the caller (a pass over a multi-GB map otherwise)
+            c_min, c_max = np.float64(self.extra["c_min"]), np.float64(self.extra["c_max"])
+        else:
+            c_min, c_max = np.float64(c.min()), np.float64(c.max())
         dim = int(stencil.matlab_round(c_max) - stencil.matlab_round(c_min))
         dm = stencil.d_map(c_min, dim, self.dt, self.dx, is_3d=self.ndim == 3)
         ndmap = 1 if dim == 0 else dm.shape[2]
@@ -170,60 +175,108 @@ def _f64(a, shape) -> np.ndarray:
     return a
 
 
+def _user_map(a, shape) -> np.ndarray:
+    """A user-grid map as the C-ABI takes it: C-contiguous float64 (the reference's Medium) or float32 as is."""
+    a = np.asarray(a)
+    a = np.ascontiguousarray(a, dtype=np.float32 if a.dtype == np.float32 else np.float64)
+    if a.shape != tuple(shape):
+        raise ValueError(f"map shape error: {a.shape} != {tuple(shape)}")
+    return a
+
+
+def marshal_medium(spec: MediumSpec):
+    """MediumSpec -> (CMedium, keepalive list, (d_table, dmap, ndmap)).  float32 user maps go through unconverted
+    (fw25_medium.input_f32) when EVERY user-grid map is float32; otherwise everything is float64."""
+    if spec.ndim not in (2, 3):
+        raise ValueError("the medium must be 2D or 3D")
+    shape = tuple(int(n) for n in spec.user_shape)
+    md = CMedium()
+    keep = []
+    user = [spec.sound_speed, spec.density, spec.beta]
+    if spec.relax is not None:
+        user += [spec.relax[k] for k in RELAX_KEYS]
+    else:
+        if spec.lut is None or spec.alpha_coeff is None or spec.alpha_power is None:
+            raise ValueError("MediumSpec needs either the relaxation maps or alpha_coeff / alpha_power + a table")
+        user += [spec.alpha_coeff, spec.alpha_power]
+    f32 = all(np.asarray(a).dtype == np.float32 for a in user)
+
+    def put(a, shp=shape, user_map=False):
+        a = _user_map(a, shp) if (user_map and f32) else _f64(a, shp)
+        keep.append(a)
+        return a.ctypes.data
+
+    md.ndim = spec.ndim
+    md.nx, md.ny, md.nz = shape[0], shape[1], shape[2] if spec.ndim == 3 else 1
+    md.m_spatial_order, md.n_pml_layer = spec.m_spatial_order, spec.n_pml_layer
+    md.n_transition_layer, md.use_pml = spec.n_transition_layer, int(spec.use_pml)
+    md.dt = spec.dt
+    md.input_f32 = int(f32)
+    if spec.use_pml:
+        md.d_target_pml = spec.d_target_pml()
+        tp, tl, tc = spec.transition_tables()
+        md.tf_polynomial, md.tf_linear, md.tf_cosine = put(tp, tp.shape), put(tl, tl.shape), put(tc, tc.shape)
+    md.sound_speed, md.density, md.beta = (put(a, user_map=True) for a in user[:3])
+    if spec.relax is not None:
+        for i, k in enumerate(RELAX_KEYS):
+            md.relax[i] = put(spec.relax[k], user_map=True)
+    else:
+        t = spec.lut
+        db = np.ascontiguousarray(t.database, dtype=np.float64)
+        if db.ndim != 3:
+            raise ValueError("look_up_table must have 3 dimensions.")
+        if db.shape[2] != 10:
+            raise ValueError("look_up_table must have 4 * n_relaxation_mechanisms + 2 columns.")
+        if np.isnan(db).any():
+            raise ValueError("look_up_table must not contain NaN values.")
+        al, pl = np.asarray(t.alpha_list, np.float64).reshape(-1), np.asarray(t.power_list, np.float64).reshape(-1)
+        md.alpha_coeff, md.alpha_power = put(spec.alpha_coeff, user_map=True), put(spec.alpha_power, user_map=True)
+        md.lut = put(db, db.shape)
+        md.lut_alpha, md.lut_power = put(al.round(10), al.shape), put(pl.round(10), pl.shape)
+        md.lut_na, md.lut_np = db.shape[0], db.shape[1]
+        md.alpha_min, md.alpha_max = float(al.min()), float(al.max())
+        md.power_min, md.power_max = float(pl.min()), float(pl.max().round(4))
+        if t.invalid_matrix is not None:
+            inv = np.ascontiguousarray(np.asarray(t.invalid_matrix) != 0, dtype=np.uint8)
+            keep.append(inv)
+            md.lut_invalid = inv.ctypes.data
+    tables = spec.stencil_tables()
+    md.c_round_min = tables[3]
+    md.dcmap_full3d = int(bool(spec.dcmap_full3d))
+    return md, keep, tables[:3]
+
+
+def run_medium(spec: MediumSpec, pb, device: int = 0):
+    """Whole job from the USER-grid medium through fw25_run_medium (C-ABI): the medium is uploaded block by block, the
+    maps are generated as the blocks land and the first time steps already run underneath.  pb: a Problem holding the
+    step counts and the coordinate lists on the EXTENDED grid (`Problem.for_device_maps`-style; its maps are unused).
+    Returns (genout [n_frames, ncoordsout], stats)."""
+    import time
+    t0 = time.perf_counter()
+    md, keep, (d_table, dmap, ndmap) = marshal_medium(spec)
+    pb.normalise()
+    s, keep2 = engine.marshal(pb, device_maps={name: 0 for name in MAP_NAMES + ("dcmap",)})
+    s.maps_on_device = 0
+    s.dmap, s.ndmap = dmap.ctypes.data, ndmap
+    genout = np.zeros((pb.n_frames, pb.ncoordsout), np.float32)
+    st = engine.CStats()
+    t1 = time.perf_counter()
+    engine._check(_lib().fw25_run_medium(C.byref(md), C.byref(s), device, genout.ctypes.data_as(engine._F), genout.size,
+                                         C.byref(st)))
+    t2 = time.perf_counter()
+    del keep, keep2
+    stats = {f: getattr(st, f) for f, _ in engine.CStats._fields_}
+    stats.update(host_marshal_ms=(t1 - t0) * 1e3, native_call_ms=(t2 - t1) * 1e3)
+    return genout, stats
+
+
 class MapSet:
     """Device-resident maps of one medium (fw25_mapset).  Keep it alive as long as an engine uses it."""
 
     def __init__(self, spec: MediumSpec, device: int = 0):
-        if spec.ndim not in (2, 3):
-            raise ValueError("the medium must be 2D or 3D")
         self.spec = spec
         self.device = device
-        shape = tuple(int(n) for n in spec.user_shape)
-        md = CMedium()
-        keep = []
-
-        def put(a, shp=shape):
-            a = _f64(a, shp)
-            keep.append(a)
-            return a.ctypes.data
-
-        md.ndim = spec.ndim
-        md.nx, md.ny, md.nz = shape[0], shape[1], shape[2] if spec.ndim == 3 else 1
-        md.m_spatial_order, md.n_pml_layer = spec.m_spatial_order, spec.n_pml_layer
-        md.n_transition_layer, md.use_pml = spec.n_transition_layer, int(spec.use_pml)
-        md.dt = spec.dt
-        if spec.use_pml:
-            md.d_target_pml = spec.d_target_pml()
-            tp, tl, tc = spec.transition_tables()
-            md.tf_polynomial, md.tf_linear, md.tf_cosine = put(tp, tp.shape), put(tl, tl.shape), put(tc, tc.shape)
-        md.sound_speed, md.density, md.beta = put(spec.sound_speed), put(spec.density), put(spec.beta)
-        if spec.relax is not None:
-            for i, k in enumerate(RELAX_KEYS):
-                md.relax[i] = put(spec.relax[k])
-        else:
-            if spec.lut is None or spec.alpha_coeff is None or spec.alpha_power is None:
-                raise ValueError("MediumSpec needs either the relaxation maps or alpha_coeff / alpha_power + a table")
-            t = spec.lut
-            db = np.ascontiguousarray(t.database, dtype=np.float64)
-            if db.ndim != 3:
-                raise ValueError("look_up_table must have 3 dimensions.")
-            if db.shape[2] != 10:
-                raise ValueError("look_up_table must have 4 * n_relaxation_mechanisms + 2 columns.")
-            if np.isnan(db).any():
-                raise ValueError("look_up_table must not contain NaN values.")
-            al, pl = np.asarray(t.alpha_list, np.float64).reshape(-1), np.asarray(t.power_list, np.float64).reshape(-1)
-            md.alpha_coeff, md.alpha_power = put(spec.alpha_coeff), put(spec.alpha_power)
-            md.lut = put(db, db.shape)
-            md.lut_alpha, md.lut_power = put(al.round(10), al.shape), put(pl.round(10), pl.shape)
-            md.lut_na, md.lut_np = db.shape[0], db.shape[1]
-            md.alpha_min, md.alpha_max = float(al.min()), float(al.max())
-            md.power_min, md.power_max = float(pl.min()), float(pl.max().round(4))
-            if t.invalid_matrix is not None:
-                inv = np.ascontiguousarray(np.asarray(t.invalid_matrix) != 0, dtype=np.uint8)
-                keep.append(inv)
-                md.lut_invalid = inv.ctypes.data
-        self.d_table, self.dmap, self.ndmap, md.c_round_min = spec.stencil_tables()
-        md.dcmap_full3d = int(bool(spec.dcmap_full3d))
+        md, keep, (self.d_table, self.dmap, self.ndmap) = marshal_medium(spec)
         h = C.c_void_p()
         ms = (C.c_double * 2)()
         engine._check(_lib().fw25_mapgen(C.byref(md), device, C.byref(h), ms))

@@ -171,3 +171,37 @@ def maps_to_host(maps: dict, nZ: int, pin: bool = True) -> dict:
         h.copy_(t[..., :nZ])
         out[name] = h
     return out
+
+
+def make_user_medium(user_shape, *, device, block: int = 24, seed: int = 1234, pin: bool = True, chunk: int = 16):
+    """The synthetic tissue medium as a USER-grid `fullwave.Medium` would hold it -- sound_speed, density, beta,
+    alpha_coeff, alpha_power -- as float32 HOST arrays (pinned), generated on the device chunk by chunk.  Input of the
+    GPU map builder (`mapgen.MediumSpec` with a look-up table).  Returns (maps, c_min, c_max)."""
+    import torch
+
+    nx, ny, nz = (int(s) for s in user_shape)
+    dev = torch.device(device)
+    f32 = torch.float32
+    tis = torch.tensor(synthetic.TISSUES, dtype=f32, device=dev)
+    ntis = tis.shape[0]
+    names = ("sound_speed", "density", "beta", "alpha_coeff", "alpha_power")
+    host = {n: torch.empty((nx, ny, nz), dtype=f32, pin_memory=pin) for n in names}
+    by = (torch.arange(ny, device=dev) // block).to(torch.int64)
+    bz = (torch.arange(nz, device=dev) // block).to(torch.int64)
+    c_min, c_max = float("inf"), float("-inf")
+    for x0 in range(0, nx, chunk):
+        x1 = min(x0 + chunk, nx)
+        gx = torch.arange(x0, x1, device=dev)
+        bx = (gx // block).to(torch.int64)
+        h = (bx[:, None, None] * 73856093) ^ (by[None, :, None] * 19349663) ^ (bz[None, None, :] * 83492791) ^ (seed * 2654435761)
+        h = (h ^ (h >> 13)) * 1274126177
+        lab = ((h ^ (h >> 16)) & 0x7FFFFFFF) % ntis
+        jit = (gx[:, None, None] * 1103515245 + torch.arange(ny, device=dev)[None, :, None] * 12345 +
+               torch.arange(nz, device=dev)[None, None, :] * 2654435761 + seed) & 0xFFFF
+        c = tis[lab, 0] + (jit.to(f32) / 65535.0 - 0.5) * 0.8
+        c_min, c_max = min(c_min, float(c.min())), max(c_max, float(c.max()))
+        for n, v in zip(names, (c, tis[lab, 1], tis[lab, 2], tis[lab, 3], tis[lab, 4])):
+            host[n][x0:x1].copy_(v, non_blocking=True)
+        torch.cuda.synchronize(dev)
+        del h, lab, jit, c
+    return {n: t.numpy() for n, t in host.items()}, c_min, c_max, host

@@ -103,7 +103,7 @@ typedef struct fw25_stats {
   int64_t point_updates;      /* nX*nY*nZ * nT (extended grid, the reference's count) */
   int64_t halo_bytes;         /* bytes moved between x-slabs (all interfaces, both directions); 0 on one device */
   int32_t n_devices;
-  int32_t reserved_;
+  int32_t skewed_steps;       /* fw25_run_medium: time steps that ran block-wise under the upload of the medium */
 } fw25_stats;
 
 typedef struct fw25_engine fw25_engine; /* opaque */

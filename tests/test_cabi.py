@@ -30,7 +30,7 @@ def test_library_loads_and_exports_every_declared_symbol(built_lib):
 
 def test_python_binding_covers_the_header(built_lib):
     assert set(engine.EXPORTS) | set(mapgen.SIGS) == set(declared_symbols())
-    assert engine.lib().fw25_abi_version() == 5
+    assert engine.lib().fw25_abi_version() == 6
     assert engine.lib().fw25_pitch(1241) == 1248
 
 
@@ -41,4 +41,4 @@ def test_struct_layout_matches_header(built_lib):
     assert ctypes.sizeof(engine.CSlab) == 16
     assert ctypes.sizeof(engine.CStats) == 8 * 8 + 2 * 4
     # fw25_medium: 8 int32, 2 double, 3 + 3 + 10 + 2 + 3 pointers, 2 int32, 4 double, 1 pointer, 2 int32
-    assert ctypes.sizeof(mapgen.CMedium) == 8 * 4 + 2 * 8 + 21 * 8 + 2 * 4 + 4 * 8 + 8 + 2 * 4
+    assert ctypes.sizeof(mapgen.CMedium) == 8 * 4 + 2 * 8 + 21 * 8 + 2 * 4 + 4 * 8 + 8 + 4 * 4
