@@ -87,29 +87,33 @@ void Engine::setup_sources(int ncoords, const int32_t *icc, const float *icmat) 
   // A plane source of a full-size 3D grid is millions of coordinates: the list is resolved by a few threads, each
   // over a contiguous range of rows, and concatenated in row order.
   struct Part {
-    std::vector<long long> idx; std::vector<int> row; std::vector<unsigned char> flag, plane;
-    int rim = 0; bool bad = false;
+    std::vector<unsigned char> plane;
+    int rim = 0, kept = 0; bool bad = false;
   };
   const int n_thr = ncoords >= (1 << 17) ? (int)std::min<unsigned>(8, std::max(1u, std::thread::hardware_concurrency())) : 1;
   std::vector<Part> parts(n_thr);
+  // every thread writes its rows in place; slab engines drop the sources of other slabs and compact afterwards
+  h_src_idx.resize((size_t)ncoords); h_src_row.resize((size_t)ncoords); h_src_flag.resize((size_t)ncoords);
   auto work = [&](int k) {
     Part &P = parts[k];
     const int i0 = (int)((long long)ncoords * k / n_thr), i1 = (int)((long long)ncoords * (k + 1) / n_thr);
     P.plane.assign((size_t)nXl, 0);
-    P.idx.reserve(i1 - i0); P.row.reserve(i1 - i0); P.flag.reserve(i1 - i0);
+    int o = i0;
     for (int i = i0; i < i1; ++i) {
       const int32_t *c = icc + (size_t)i * nd;
       if (!coord_ok(c)) { P.bad = true; return; }
       if (c[0] < gx0 || c[0] >= gx0 + nXl) continue;
       const long long li = lin(c[0], c[1], nd == 3 ? c[2] : 0);
-      P.idx.push_back(li);
-      P.row.push_back(i);
       const bool r = is_rim(c[0], c[1], nd == 3 ? c[2] : M);
       const bool dead = plane_air[c[0] - gx0] && air_set.count(li) != 0;
-      P.flag.push_back((unsigned char)((r ? 1 : 0) | (dead ? 2 : 0)));
+      h_src_idx[o] = li;
+      h_src_row[o] = i;
+      h_src_flag[o] = (unsigned char)((r ? 1 : 0) | (dead ? 2 : 0));
+      ++o;
       P.rim += (r && !dead);
       if (!dead) P.plane[c[0] - gx0] = 1;
     }
+    P.kept = o - i0;
   };
   {
     std::vector<std::thread> th;
@@ -117,15 +121,21 @@ void Engine::setup_sources(int ncoords, const int32_t *icc, const float *icmat) 
     work(0);
     for (auto &t_ : th) t_.join();
   }
-  h_src_idx.clear(); h_src_row.clear(); h_src_flag.clear();
-  for (Part &P : parts) {
+  size_t out = 0;
+  for (int k = 0; k < n_thr; ++k) {
+    Part &P = parts[k];
     if (P.bad) fail(1, "icc: source coordinate outside the grid");
-    h_src_idx.insert(h_src_idx.end(), P.idx.begin(), P.idx.end());
-    h_src_row.insert(h_src_row.end(), P.row.begin(), P.row.end());
-    h_src_flag.insert(h_src_flag.end(), P.flag.begin(), P.flag.end());
+    const size_t i0 = (size_t)((long long)ncoords * k / n_thr);
+    if (out != i0 && P.kept) {
+      std::move(h_src_idx.begin() + i0, h_src_idx.begin() + i0 + P.kept, h_src_idx.begin() + out);
+      std::move(h_src_row.begin() + i0, h_src_row.begin() + i0 + P.kept, h_src_row.begin() + out);
+      std::move(h_src_flag.begin() + i0, h_src_flag.begin() + i0 + P.kept, h_src_flag.begin() + out);
+    }
+    out += P.kept;
     n_src_rim += P.rim;
     for (int a = 0; a < nXl; ++a) plane_src[a] |= P.plane[a];
   }
+  h_src_idx.resize(out); h_src_row.resize(out); h_src_flag.resize(out);
   n_src = (int)h_src_idx.size();
   d_src_idx = salloc<long long>(n_src); d_src_row = salloc<int>(n_src); d_src_rim = salloc<unsigned char>(n_src);
   d_icmat = nullptr;

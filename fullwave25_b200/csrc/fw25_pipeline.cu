@@ -7,14 +7,17 @@
 // lands (MapStream, fw25_mapgen.cu), and the x-marching sweeps start on the blocks that are ready.
 //
 // Time skew.  fd_u(t) at plane x reads p_t at x-7 .. x+8, fd_p(t) reads u_{t+1} at x-8 .. x+7 (and v, w at x +- 1), and
-// both update in place.  With blocks of B >= 16 planes, step t may therefore run one block behind its own fd_u and
-// two blocks behind step t-1:
+// both update in place.  With blocks of B = 32 planes, U(m) = [B m, B (m+1)) and the half-block-shifted ranges
+// P(m) = [B m - 16, B (m+1) - 16), step t can run ONE block behind step t-1:
 //
-//     stage k:   for t = 0, 1, 2, ...   m = k - 2 t
-//                  inject(t)  on block m+1      (p_t there is final: fd_p(t-1) passed it earlier in this stage)
-//                  fd_u(t)    on block m        (reads p_t up to 8 planes into block m+1, 7 planes into block m-1)
-//                  fd_p(t)    on block m-1      (reads u_{t+1} of blocks m-2 .. m; block m-2 is overwritten by
-//                  record(t)  on block m-1       fd_u(t+1) only later in this stage)
+//     stage k:   for t = 0, 1, 2, ...   m = k - t
+//                  fd_u(t)      on U(m)      reads p_t on [B m - 7, B (m+1) + 8]: P(m) (final and injected since stage
+//                                            k-1, overwritten by fd_p(t) only below) and P(m+1) (fd_p(t-1) and
+//                                            inject(t) passed it earlier in THIS stage)
+//                  fd_p(t)      on P(m)      reads u_{t+1} on [B m - 24, B m + 23]: U(m-1), U(m); U(m-1) is overwritten
+//                                            by fd_u(t+1) only later in this stage
+//                  record(t)    on P(m)      the freshly updated p, before the next injection touches it
+//                  inject(t+1)  on P(m)      p_{t+1} there is final now
 //
 // Stage k touches maps of blocks <= k only, so it can be queued as soon as block k has been generated; everything runs
 // on ONE stream in this order, which is what makes the in-place update safe.  Every cell sees exactly the operations,
@@ -35,45 +38,50 @@ bool Engine::skew_supported(int Ts) const {
 }
 
 void Engine::run_skewed(int Ts, int block, const std::function<cudaEvent_t(int)> &avail) {
-  if (block < 2 * M) fail(1, "run_skewed: blocks must hold at least 16 planes");
+  if (block < 4 * M || block % 2) fail(1, "run_skewed: blocks must hold an even number of >= 32 planes");
   if (t != 0) fail(1, "run_skewed: the engine has already stepped");
-  const int NB = (G.nA + block - 1) / block;
-  auto lo = [&](int b) { return b * block; };                       // local planes of block b
-  auto hi = [&](int b) { return std::min((b + 1) * block, G.nA); };
-  auto any = [&](const std::vector<unsigned char> &flag, int b) {
-    for (int a = lo(b); a < hi(b); ++a)
+  const int NB = (G.nA + block - 1) / block, H = block / 2;
+  struct Range { int lo, hi; };                                     // local planes
+  auto U = [&](int m) { return Range{m * block, std::min((m + 1) * block, G.nA)}; };
+  auto P = [&](int m) { return Range{std::min(std::max(m * block - H, 0), G.nA), std::min((m + 1) * block - H, G.nA)}; };
+  auto any = [&](const std::vector<unsigned char> &flag, Range r) {
+    for (int a = r.lo; a < r.hi; ++a)
       if (flag[a]) return true;
     return false;
   };
-  auto inject_block = [&](int tt, int b) {
-    const bool src = n_src > 0 && (tt < nTic || n_src_rim > 0) && any(plane_src, b);
-    const bool air = n_air > 0 && any(plane_air, b);
+  auto inject_range = [&](int tt, Range r) {
+    if (r.hi <= r.lo) return;
+    const bool src = n_src > 0 && (tt < nTic || n_src_rim > 0) && any(plane_src, r);
+    const bool air = n_air > 0 && any(plane_air, r);
     if (!src && !air) return;
     launch_inject_range(F.p, d_src_idx, d_src_row, d_src_rim, src ? n_src : 0, d_icmat, nTic, tt, d_air_idx,
-                        air ? n_air : 0, G.sA, lo(b), hi(b), stream);
+                        air ? n_air : 0, G.sA, r.lo, r.hi, stream);
     ++launches;
   };
-  for (int k = 0; k <= NB + 2 * (Ts - 1); ++k) {
+  for (int k = 0; k <= NB + Ts - 1; ++k) {
     if (k < NB) {
       cudaEvent_t ev = avail(k);
       if (!ev) throw Fail{2};
       FW_CUDA(cudaStreamWaitEvent(stream, ev, 0));
     }
     for (int tt = 0; tt < Ts; ++tt) {
-      const int m = k - 2 * tt;
-      if (m < -1) break;
+      const int m = k - tt;
+      if (m < 0) break;
       if (m > NB) continue;                                         // step tt is complete
-      if (m == 0 && tt == 0) inject_block(0, 0);
-      if (m + 1 < NB) inject_block(tt, m + 1);
-      if (m >= 0 && m < NB) sweep_u(gx0 + lo(m), gx0 + hi(m), stream);
-      if (m >= 1 && m - 1 < NB) {
-        sweep_p(gx0 + lo(m - 1), gx0 + hi(m - 1), stream);
-        if (tt % modT == 0 && n_sens > 0 && any(plane_sens, m - 1)) {
-          launch_record_range(F.p, d_sens_idx, n_sens, d_frames + (size_t)((tt / modT) % frames_cap) * n_sens, G.sA,
-                              lo(m - 1), hi(m - 1), stream);
-          ++launches;
-        }
+      if (tt == 0) {                                                // nobody injects for step 0 behind a fd_p
+        if (m == 0) inject_range(0, P(0));
+        if (m + 1 <= NB) inject_range(0, P(m + 1));
       }
+      if (m < NB) { const Range r = U(m); sweep_u(gx0 + r.lo, gx0 + r.hi, stream); }
+      const Range r = P(m);
+      if (r.hi <= r.lo) continue;
+      sweep_p(gx0 + r.lo, gx0 + r.hi, stream);
+      if (tt % modT == 0 && n_sens > 0 && any(plane_sens, r)) {
+        launch_record_range(F.p, d_sens_idx, n_sens, d_frames + (size_t)((tt / modT) % frames_cap) * n_sens, G.sA, r.lo,
+                            r.hi, stream);
+        ++launches;
+      }
+      if (tt + 1 < Ts) inject_range(tt + 1, r);
     }
   }
   FW_CUDA(cudaGetLastError());
@@ -124,7 +132,7 @@ int run_medium(const fw25_medium *md, const fw25_problem *pb_in, int device, flo
   const double setup_ms = ms_since(t0);
   const int NB = mapstream_blocks(H.S);
   // steps that can start before the last block has arrived; the rest run as whole-grid sweeps
-  int Ts = std::min(e.nT, (NB + 1) / 2);
+  int Ts = std::min(e.nT, NB);
   if (const char *ev = getenv("FW25_SKEW_STEPS")) Ts = std::min(e.nT, std::max(0, atoi(ev)));   // tests / A-B runs
   const int64_t l0 = e.launches;
   cudaEvent_t ev_a = nullptr, ev_b = nullptr;

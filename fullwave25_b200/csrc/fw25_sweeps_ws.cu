@@ -14,6 +14,7 @@
 // Replaces fd_u / fd_p (3D PTX L38-675 / L677-1323).
 #include <cuda.h>
 
+#include <algorithm>
 #include <cstddef>
 #include <cstdio>
 #include <cstdlib>
@@ -65,6 +66,24 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
 }
 
+// Tile order.  CTAs are handed out in blockIdx.x-fastest order and about 2 x 148 of them are resident: a CTA starts
+// when the one ~296 launches before it retires, so two tiles that are d launches apart run ~ d / 296 chunks out of
+// phase.  With z fastest over a full row of tiles (39 at nZ = 1240), y-neighbours are 39 launches = 4 planes apart and
+// the y halo rows one of them brought into L2 are gone (~13 MB stream through L2 per plane step) by the time the other
+// asks for them.  Strips of `strip` z-tiles (z fastest inside the strip, then y, then the next strip) put y-neighbours
+// `strip` launches apart; only the strip edges (1 in `strip` z-halos) are out of phase.
+__device__ __forceinline__ void tile_of_block(int strip, int &bx, int &by) {
+  bx = blockIdx.x; by = blockIdx.y;
+  if (strip <= 0 || strip >= (int)gridDim.x) return;
+  const int L = blockIdx.x + gridDim.x * blockIdx.y;
+  const int per = strip * gridDim.y;
+  const int s = L / per;
+  const int w = min(strip, (int)gridDim.x - s * strip);     // the last strip may be narrower
+  const int r = L - s * per;
+  by = r / w;
+  bx = s * strip + r - by * w;
+}
+
 template <int TY>
 struct alignas(128) SmemU {
   float halo[NH][TY + 2 * M][TZ + 2 * M];
@@ -97,7 +116,10 @@ __global__ void __launch_bounds__((TY + 1) * TZ, MINB)
   constexpr uint32_t HALO_BYTES = HY * HZ * 4, PW_BYTES = NPW_U * TY * TZ * 4;
 
   const int tz = threadIdx.x, ty = threadIdx.y;
-  const int z0 = blockIdx.x * TZ, y0 = M + blockIdx.y * TY;
+  int bx, by;
+  tile_of_block(hint >> 8, bx, by);
+  hint &= 0xff;
+  const int z0 = bx * TZ, y0 = M + by * TY;
   const int xa = a_lo + blockIdx.z * Lx;
   const int xb = min(xa + Lx, a_hi);
   const int len = xb - xa;
@@ -263,7 +285,10 @@ __global__ void __launch_bounds__((TY + 1) * TZ, MINB)
                      W_BYTES = (TY + 2) * (TZ + 2 * M) * 4, PW_BYTES = NPW_P * TY * TZ * 4;
 
   const int tz = threadIdx.x, ty = threadIdx.y;
-  const int z0 = blockIdx.x * TZ, y0 = M + blockIdx.y * TY;
+  int bx, by;
+  tile_of_block(hint >> 8, bx, by);
+  hint &= 0xff;
+  const int z0 = bx * TZ, y0 = M + by * TY;
   const int xa = a_lo + blockIdx.z * Lx;
   const int xb = min(xa + Lx, a_hi);
   const int len = xb - xa;
@@ -452,8 +477,14 @@ constexpr int MINB_WS = FW25_WS_MINB;
 
 // 1: point-wise tiles are loaded with an L2 evict-first policy.  Helps long chunks, costs ~2 % at the default
 // chunk length (profiles/sweep_lx_r01.txt), so it is off by default.
+// bits 8..: strip width of the tile order (tile_of_block); 0 = plain z-fastest order
 int ws_hint() {
-  static const int h = [] { const char *e = getenv("FW25_WS_HINT"); return e ? atoi(e) : 0; }();
+  static const int h = [] {
+    const char *e = getenv("FW25_WS_HINT");
+    const char *s = getenv("FW25_WS_STRIP");
+    const int strip = s ? atoi(s) : 8;
+    return (e ? atoi(e) & 0xff : 0) | (std::max(strip, 0) << 8);
+  }();
   return h;
 }
 

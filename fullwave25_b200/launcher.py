@@ -30,7 +30,22 @@ logger = logging.getLogger("__main__." + __name__)
 
 
 class SimulationError(Exception):
-    """Raised when the engine fails (the reference raises its own SimulationError on a non-zero exit status)."""
+    """Raised when the engine fails (the reference raises its own SimulationError on a non-zero exit status).
+    After `install()` the raised class ALSO derives from `fullwave.solver.launcher.SimulationError`, so user code
+    that catches the reference's exception keeps working."""
+
+
+_raise_cls = SimulationError          # install() swaps in a subclass of both error types
+_reference_launcher_cls = None        # the reference's own Launcher, kept by install() for the runs this engine does not cover
+
+
+def _sim_error(msg: str) -> Exception:
+    return _raise_cls(msg)
+
+
+def _is_exponential_attenuation_dir(simulation_dir: Path) -> bool:
+    """The exponential-attenuation file set (input_file_writer.py:629-650, :746-751): a_exp.dat, no relaxation maps."""
+    return (simulation_dir / "a_exp.dat").exists() and not (simulation_dir / "kappax.dat").exists()
 
 
 def parse_cuda_device_id(cuda_device_id) -> str:
@@ -66,8 +81,9 @@ def device_ids_of(cuda_device_id) -> tuple[int, ...]:
 # files resolve to the same files (same real path, size and mtime), only the source list is replaced
 # (fw25_reset) and the maps never leave HBM.
 
-_STATIC_FILES = MAP_NAMES + ("dcmap", "dmap", "outc", "icczero", "nX", "nY", "nZ", "modT", "dX", "dT", "ndmap",
-                             "ncoordsout", "ncoordszero")
+_STATIC_FILES = (MAP_NAMES + Problem.aniso_stems(3) +
+                 ("dcmap", "dmap", "c", "outc", "icczero", "nX", "nY", "nZ", "modT", "dX", "dT", "ndmap", "ncoordsout",
+                  "ncoordszero"))
 
 
 def _static_key(simulation_dir: Path, device_ids) -> tuple | None:
@@ -82,8 +98,8 @@ def _static_key(simulation_dir: Path, device_ids) -> tuple | None:
         if not f.exists():
             key.append((stem, None))
             continue
-        st = f.stat()
-        key.append((stem, os.path.realpath(f), st.st_size, st.st_mtime_ns))
+        st = f.stat()      # (follows the link: identity and change times of the work directory's file)
+        key.append((stem, os.path.realpath(f), st.st_ino, st.st_size, st.st_mtime_ns, st.st_ctime_ns))
     return tuple(key)
 
 
@@ -119,6 +135,7 @@ def _run_dat_dir(simulation_dir: Path, device_ids) -> tuple[np.ndarray, dict]:
         return genout, stats
     pb = Problem.from_dat_dir(simulation_dir)
     if key is None:
+        release()                 # a kept engine holds its maps + state in HBM: this run needs the memory
         return engine.run(pb, device_ids=device_ids)
     _LiveEngine.release()
     eng = engine.Engine(pb, device=device_ids[0])
@@ -154,7 +171,7 @@ class Launcher:
 
     def __init__(self, path_fullwave_simulation_bin: Path | None = None, *, is_3d: bool = False,
                  use_gpu: bool = True, cuda_device_id=None) -> None:
-        self._path_fullwave_simulation_bin = path_fullwave_simulation_bin   # kept for interface parity; unused
+        self._path_fullwave_simulation_bin = path_fullwave_simulation_bin   # used only by runs handed to the reference
         self.is_3d = is_3d
         self.use_gpu = use_gpu
         self.cuda_device_id = parse_cuda_device_id(cuda_device_id)
@@ -165,6 +182,17 @@ class Launcher:
         simulation_dir = Path(simulation_dir).absolute()
         if not self.use_gpu:
             raise NotImplementedError("Currently, only GPU version is supported.")
+        if _is_exponential_attenuation_dir(simulation_dir):
+            # not this engine's physics (out of scope): hand the run to the reference's own launcher
+            # and binary, which is what `install()` promises for such solvers
+            ref_cls = _reference_launcher_cls
+            if ref_cls is None:
+                raise NotImplementedError("exponential-attenuation simulations run on the reference engine only; "
+                                          "call fullwave25_b200.launcher.install() or use fullwave's Launcher")
+            ref = ref_cls(self._path_fullwave_simulation_bin, is_3d=self.is_3d, use_gpu=self.use_gpu,
+                          cuda_device_id=[int(v) for v in self.cuda_device_id.split(",")]
+                          if "," in self.cuda_device_id else int(self.cuda_device_id))
+            return ref.run(simulation_dir, load_results=load_results)
         log = simulation_dir / "fw2_execution.log"
         t0 = time.time()
         try:
@@ -177,7 +205,7 @@ class Launcher:
             msg = ("Simulation failed. please check the simulation log file for more information.\n"
                    f"The log file is located at:\n{log}")
             logger.exception(msg)
-            raise SimulationError(msg) from e
+            raise _sim_error(msg) from e
         self.last_stats = stats
         genout.tofile(simulation_dir / "genout.dat")
         log.write_text(f"fw25 engine (libfw25.so, sm_100a)\n{stats}\nSimulation completed in {time.time() - t0:.2e} s\n")
@@ -218,9 +246,16 @@ def install(fullwave_module=None, *, in_memory: bool = False, maps: str = "host"
     import weakref
     if maps not in ("host", "device"):
         raise ValueError('maps must be "host" or "device"')
+    global _raise_cls, _reference_launcher_cls
     sol = importlib.import_module("fullwave.solver.solver")
     lau = importlib.import_module("fullwave.solver.launcher")
     saved = (sol.Launcher, lau.Launcher, sol.Solver.run, sol.PMLBuilder)
+    saved_err = (_raise_cls, _reference_launcher_cls)
+    if lau.Launcher is not Launcher:
+        _reference_launcher_cls = lau.Launcher
+    ref_err = getattr(lau, "SimulationError", None)
+    if isinstance(ref_err, type) and not issubclass(SimulationError, ref_err):
+        _raise_cls = type("SimulationError", (SimulationError, ref_err), {})
     sol.Launcher = Launcher
     lau.Launcher = Launcher
 
@@ -252,7 +287,9 @@ def install(fullwave_module=None, *, in_memory: bool = False, maps: str = "host"
             sol.PMLBuilder = lazy_pml_builder_class(sol.PMLBuilder)
 
     def uninstall():
+        global _raise_cls, _reference_launcher_cls
         sol.Launcher, lau.Launcher, sol.Solver.run, sol.PMLBuilder = saved
+        _raise_cls, _reference_launcher_cls = saved_err
         _StaticSession.release()
     return uninstall
 
@@ -380,10 +417,12 @@ def run_solver(solver, *, record_whole_domain: bool = False, sampling_modulus_ti
     ids = device_ids_of(cuda_device_id if cuda_device_id is not None else getattr(solver, "cuda_device_id", None))
     if maps == "device" and len(ids) == 1 and not (session is not None and session.eng is not None):
         sensor, out_box = _sensor_and_box(solver, record_whole_domain, sampling_modulus_time_whole_domain, lean=True)
+        if session is None:
+            release()             # an engine kept for static-map reuse would only be in the way
         try:
             genout, stats, pb = _run_solver_device_maps(solver, sensor, out_box, ids[0], session)
-        except engine.EngineError as e:
-            raise SimulationError(str(e)) from e
+        except (engine.EngineError, ValueError) as e:
+            raise _sim_error(str(e)) from e
         result = genout.reshape(-1, pb.ncoordsout).T
         return (result, stats) if return_stats else result
     if session is not None and session.eng is not None:      # next transmit event: only the sources change
@@ -392,11 +431,23 @@ def run_solver(solver, *, record_whole_domain: bool = False, sampling_modulus_ti
         shape = (eg.nx, eg.ny, eg.nz) if solver.is_3d else (eg.nx, eg.ny)
         if tuple(shape) != tuple(session.shape):
             raise ValueError(f"session holds a {session.shape} grid, this solver has {shape}")
+        # only the SOURCE may change between the events of a session: sensors, recording period and (by contract)
+        # the medium stay on the device from the first event
+        sensor, out_box = _sensor_and_box(solver, record_whole_domain, sampling_modulus_time_whole_domain, lean=True)
+        held = session.eng.pb
+        n_new = int(np.prod(np.asarray(out_box).reshape(2, -1)[1] - np.asarray(out_box).reshape(2, -1)[0])) \
+            if out_box is not None else len(np.asarray(sensor.outcoords))
+        if (n_new != held.ncoordsout or int(sensor.sampling_modulus_time) != held.modT or
+                (None if out_box is None else tuple(int(v) for v in out_box)) != held.out_box or
+                (out_box is None and not np.array_equal(np.asarray(sensor.outcoords, np.int32).reshape(-1, held.ndim),
+                                                        held.outc))):
+            raise ValueError("session: the sensor, its sampling modulus or the recording mode differs from the event "
+                             "that created the session; close it and start a new one")
         try:
             session.eng.reset(np.asarray(src.incoords), np.asarray(src.icmat), int(eg.nt))
             genout, stats = session.eng.run()
-        except engine.EngineError as e:
-            raise SimulationError(str(e)) from e
+        except (engine.EngineError, ValueError) as e:
+            raise _sim_error(str(e)) from e
         result = genout.reshape(-1, session.eng.pb.ncoordsout).T
         return (result, stats) if return_stats else result
     extended_medium = solver.pml_builder.run(use_pml=solver.use_pml)
@@ -409,8 +460,9 @@ def run_solver(solver, *, record_whole_domain: bool = False, sampling_modulus_ti
             session.shape = pb.shape
             genout, stats = session.eng.run()
         else:
+            release()
             genout, stats = engine.run(pb, device_ids=ids)
-    except engine.EngineError as e:
-        raise SimulationError(str(e)) from e
+    except (engine.EngineError, ValueError) as e:
+        raise _sim_error(str(e)) from e
     result = genout.reshape(-1, pb.ncoordsout).T          # solver.py:600-618
     return (result, stats) if return_stats else result

@@ -215,6 +215,19 @@ def test_static_map_transmit_events_reuse_device_maps(built_lib, shape):
                 s = fw.Solver(Path(td_new) / "nodisk", grid, medium, src, sensor,
                               path_fullwave_simulation_bin=build.CLI, **kw)
                 nodisk.append(launcher.run_solver(s, session=ses))
+            # a session holds sensors and recording period of its first event: a different Sensor is refused, not
+            # silently answered with the old sensor's traces
+            smask = np.asarray(sensor.mask).copy()
+            smask.flat[np.flatnonzero(~smask)[:3]] = True
+            other = fw.Solver(Path(td_new) / "nodisk2", grid, medium, sources[0],
+                              fw.Sensor(mask=smask, sampling_modulus_time=2), path_fullwave_simulation_bin=build.CLI, **kw)
+            with pytest.raises(ValueError, match="session"):
+                launcher.run_solver(other, session=ses)
+            slower = fw.Solver(Path(td_new) / "nodisk3", grid, medium, sources[0],
+                               fw.Sensor(mask=np.asarray(sensor.mask), sampling_modulus_time=3),
+                               path_fullwave_simulation_bin=build.CLI, **kw)
+            with pytest.raises(ValueError, match="session"):
+                launcher.run_solver(slower, session=ses)
     assert np.abs(want[0]).max() > 0 and not np.array_equal(want[0], want[1])
     assert not np.array_equal(want[0], want_air[0])          # the static-map directory lost the air voxels
     for k in range(3):
@@ -330,3 +343,67 @@ def test_install_in_memory_patches_and_restores_the_reference(built_lib, tmp_pat
         undo()
     assert (sol.Launcher, sol.Solver.run, sol.PMLBuilder) == before
     assert engine.lib() is not None
+
+
+@needs_ref
+def test_installed_errors_are_caught_as_the_reference_exception(built_lib, tmp_path):
+    """CPU: after install() an engine failure raises a class that `except fullwave.solver.launcher.SimulationError`
+    catches (and `except fullwave25_b200.launcher.SimulationError` too); uninstall() restores the plain class."""
+    import importlib
+    lau = importlib.import_module("fullwave.solver.launcher")
+    ref_err = lau.SimulationError
+    undo = launcher.install()
+    try:
+        (tmp_path / "nX.dat").write_bytes(b"")                   # a directory the engine cannot read
+        la = launcher.Launcher(None, is_3d=False, use_gpu=True, cuda_device_id=0)
+        with pytest.raises(ref_err) as info:
+            la.run(tmp_path)
+        assert isinstance(info.value, launcher.SimulationError)
+    finally:
+        undo()
+    assert launcher._raise_cls is launcher.SimulationError and launcher._reference_launcher_cls is None
+
+
+def test_exponential_attenuation_directory_goes_to_the_reference_launcher(built_lib, tmp_path, monkeypatch):
+    """CPU: a simulation directory of the exponential-attenuation engine (a_exp.dat, no relaxation maps) is handed to
+    the reference's own Launcher with the same arguments -- what install() promises for such solvers."""
+    calls = []
+
+    class FakeReferenceLauncher:
+        def __init__(self, path, *, is_3d, use_gpu, cuda_device_id):
+            calls.append(("init", path, is_3d, use_gpu, cuda_device_id))
+
+        def run(self, simulation_dir, *, load_results=True):
+            calls.append(("run", Path(simulation_dir), load_results))
+            return "reference result"
+
+    (tmp_path / "a_exp.dat").write_bytes(b"\0" * 16)
+    la = launcher.Launcher(Path("/some/exp_binary"), is_3d=True, use_gpu=True, cuda_device_id=[0, 1])
+    with pytest.raises(NotImplementedError):                     # not installed: nobody to hand the run to
+        la.run(tmp_path)
+    monkeypatch.setattr(launcher, "_reference_launcher_cls", FakeReferenceLauncher)
+    assert la.run(tmp_path, load_results=False) == "reference result"
+    assert calls == [("init", Path("/some/exp_binary"), True, True, [0, 1]), ("run", tmp_path.absolute(), False)]
+    (tmp_path / "kappax.dat").write_bytes(b"")                  # relaxation maps present: this engine's directory
+    assert not launcher._is_exponential_attenuation_dir(tmp_path)
+
+
+def test_static_key_sees_rewritten_maps(tmp_path):
+    """CPU: the identity of a static-map directory includes inode and change time of every linked map (and the
+    anisotropic stems), so maps rewritten in place are not mistaken for the ones on the device."""
+    work, sim = tmp_path / "work", tmp_path / "sim"
+    work.mkdir(); sim.mkdir()
+    for stem in ("rho", "kappay", "c"):
+        (work / f"{stem}.dat").write_bytes(b"\1" * 64)
+        (sim / f"{stem}.dat").symlink_to(work / f"{stem}.dat")
+    k0 = launcher._static_key(sim, (0,))
+    assert k0 is not None and launcher._static_key(sim, (0,)) == k0
+    for stem in ("kappay", "c"):
+        tmp = work / f"{stem}.tmp"
+        tmp.write_bytes(b"\2" * 64)                               # same size, new inode
+        tmp.replace(work / f"{stem}.dat")
+        assert launcher._static_key(sim, (0,)) != k0
+        k0 = launcher._static_key(sim, (0,))
+    (sim / "rho.dat").unlink()
+    (sim / "rho.dat").write_bytes(b"\1" * 64)                    # not a link: not the static-map layout
+    assert launcher._static_key(sim, (0,)) is None
