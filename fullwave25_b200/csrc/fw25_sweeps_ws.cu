@@ -137,6 +137,7 @@ __global__ void __launch_bounds__((TY + 1) * TZ, MINB)
     // ---------------- producer warp: one lane issues every load of the chunk
     if (tz == 0) {
       const uint64_t pol_stream = l2_policy_evict_first();
+      const uint64_t pol_keep = l2_policy_evict_last();
       // halo tiles of planes xa .. xb (ring index m), point-wise tiles of xa .. xb-1 one plane behind them, so
       // that waiting for a point-wise stage to drain never delays the next halo tile
       for (int m = 0; m <= len + 1; ++m) {
@@ -144,15 +145,18 @@ __global__ void __launch_bounds__((TY + 1) * TZ, MINB)
           const int s = m & (NH - 1), k = m / NH;
           if (k > 0) mbar_wait(&S.empty_h[s], (k - 1) & 1);
           mbar_arrive_expect_tx(&S.full_h[s], HALO_BYTES);
-          tma_load_3d(&S.halo[s][0][0], &maps[MU_PHALO], z0 - M, y0 - M, xa + m, &S.full_h[s]);
+          if (hint & 2) tma_load_3d_hint(&S.halo[s][0][0], &maps[MU_PHALO], z0 - M, y0 - M, xa + m, &S.full_h[s], pol_keep);
+          else tma_load_3d(&S.halo[s][0][0], &maps[MU_PHALO], z0 - M, y0 - M, xa + m, &S.full_h[s]);
         }
         const int n = m - 1;
         if (n >= 0 && n < len) {
           const int P = xa + n, s = n & (NP - 1), k = n / NP;
           if (k > 0) mbar_wait(&S.empty_p[s], (k - 1) & 1);
           mbar_arrive_expect_tx(&S.full_p[s], PW_BYTES);
-          tma_load_3d(&S.pw[s][0][0][0], &maps[MU_PNEW], z0, y0, P + M, &S.full_p[s]);   // p[x+8]: stays in L2
-          if (hint) {
+          // p[x+8] is this plane's first touch from DRAM; the haloed tile of the same plane follows 8 steps later
+          if (hint & 2) tma_load_3d_hint(&S.pw[s][0][0][0], &maps[MU_PNEW], z0, y0, P + M, &S.full_p[s], pol_keep);
+          else tma_load_3d(&S.pw[s][0][0][0], &maps[MU_PNEW], z0, y0, P + M, &S.full_p[s]);
+          if (hint & 1) {
 #pragma unroll
             for (int a = 1; a < NPW_U; ++a)
               tma_load_3d_hint(&S.pw[s][a][0][0], &maps[MU_PNEW + a], z0, y0, P, &S.full_p[s], pol_stream);
@@ -306,22 +310,30 @@ __global__ void __launch_bounds__((TY + 1) * TZ, MINB)
     // producer: halo tiles of planes xa-1 .. xb (ring index m = plane - (xa-1)), point-wise tiles of xa .. xb-1
     if (tz == 0) {
       const uint64_t pol_stream = l2_policy_evict_first();
+      const uint64_t pol_keep = l2_policy_evict_last();
       for (int m = 0; m <= len + 1; ++m) {
         {
           const int P = xa - 1 + m, s = m & (NH - 1), k = m / NH;
           if (k > 0) mbar_wait(&S.empty_h[s], (k - 1) & 1);
           mbar_arrive_expect_tx(&S.full_h[s], U_BYTES + V_BYTES + W_BYTES);
-          tma_load_3d(&S.halo[s].u[0][0], &maps[MP_UHALO], z0 - 4, y0 - 1, P, &S.full_h[s]);
-          tma_load_3d(&S.halo[s].v[0][0], &maps[MP_VHALO], z0 - 4, y0 - M, P, &S.full_h[s]);
-          tma_load_3d(&S.halo[s].w[0][0], &maps[MP_WHALO], z0 - M, y0 - 1, P, &S.full_h[s]);
+          if (hint & 2) {
+            tma_load_3d_hint(&S.halo[s].u[0][0], &maps[MP_UHALO], z0 - 4, y0 - 1, P, &S.full_h[s], pol_keep);
+            tma_load_3d_hint(&S.halo[s].v[0][0], &maps[MP_VHALO], z0 - 4, y0 - M, P, &S.full_h[s], pol_keep);
+            tma_load_3d_hint(&S.halo[s].w[0][0], &maps[MP_WHALO], z0 - M, y0 - 1, P, &S.full_h[s], pol_keep);
+          } else {
+            tma_load_3d(&S.halo[s].u[0][0], &maps[MP_UHALO], z0 - 4, y0 - 1, P, &S.full_h[s]);
+            tma_load_3d(&S.halo[s].v[0][0], &maps[MP_VHALO], z0 - 4, y0 - M, P, &S.full_h[s]);
+            tma_load_3d(&S.halo[s].w[0][0], &maps[MP_WHALO], z0 - M, y0 - 1, P, &S.full_h[s]);
+          }
         }
         const int n = m - 1;           // point-wise plane xa + n goes out right after halo plane xa + n
         if (n >= 0 && n < len) {
           const int P = xa + n, s = n & (NP - 1), k = n / NP;
           if (k > 0) mbar_wait(&S.empty_p[s], (k - 1) & 1);
           mbar_arrive_expect_tx(&S.full_p[s], PW_BYTES);
-          tma_load_3d(&S.pw[s][0][0][0], &maps[MP_UNEW], z0, y0, P + M - 1, &S.full_p[s]);   // u[x+7]: stays in L2
-          if (hint) {
+          if (hint & 2) tma_load_3d_hint(&S.pw[s][0][0][0], &maps[MP_UNEW], z0, y0, P + M - 1, &S.full_p[s], pol_keep);
+          else tma_load_3d(&S.pw[s][0][0][0], &maps[MP_UNEW], z0, y0, P + M - 1, &S.full_p[s]);   // u[x+7]
+          if (hint & 1) {
 #pragma unroll
             for (int a = 1; a < NPW_P; ++a)
               tma_load_3d_hint(&S.pw[s][a][0][0], &maps[MP_UNEW + a], z0, y0, P, &S.full_p[s], pol_stream);
@@ -475,15 +487,20 @@ bool tmap3d(CUtensorMap *m, const void *base, const Geom &G, int box_c, int box_
 constexpr int TY_WS = FW25_WS_TY;
 constexpr int MINB_WS = FW25_WS_MINB;
 
-// 1: point-wise tiles are loaded with an L2 evict-first policy.  Helps long chunks, costs ~2 % at the default
-// chunk length (profiles/sweep_lx_r01.txt), so it is off by default.
+// bit 0: point-wise tiles are loaded with an L2 evict-first policy.  Helps long chunks, costs ~2 % at the default chunk
+//        length (profiles/sweep_lx_r01.txt): off.
+// bit 1: the stencil field's tiles (p in fd_u; u, v, w in fd_p) are loaded with an L2 evict-last policy: every plane of
+//        the field is fetched twice, 7-8 plane steps apart (as the leading value of the register column, then as the
+//        haloed tile), and ~100 MB of point-wise tiles stream through L2 in between.  Measured at 800 x 1240 x 1240:
+//        27.66 -> 28.03 Gpt/s, DRAM bytes per updated point 113.5 -> 112.2 (fd_u), 107.1 -> 105.8 (fd_p)
+//        (profiles/ncu_r02_ws.txt): on by default.
 // bits 8..: strip width of the tile order (tile_of_block); 0 = plain z-fastest order
 int ws_hint() {
   static const int h = [] {
     const char *e = getenv("FW25_WS_HINT");
     const char *s = getenv("FW25_WS_STRIP");
-    const int strip = s ? atoi(s) : 8;
-    return (e ? atoi(e) & 0xff : 0) | (std::max(strip, 0) << 8);
+    const int strip = s ? atoi(s) : 0;      // measured: strips lose 4-10 % at 800 x 1240 x 1240 (profiles/README.md)
+    return (e ? atoi(e) & 0xff : 2) | (std::max(strip, 0) << 8);
   }();
   return h;
 }

@@ -55,8 +55,11 @@ def write_mat(path: str | Path) -> Path:
 
 
 def install_into(package_root: str | Path) -> Path:
-    """Write the stand-in where `fullwave.Medium` looks for the database (package_root contains `fullwave/`)."""
-    return write_mat(Path(package_root) / "fullwave" / "utils" / "bins" / "database" / DB_NAME)
+    """Write the stand-in where `fullwave.Medium` and the medium-builder domains look for the database
+    (fullwave/solver/bins/database/, medium.py:776-780; package_root contains `fullwave/`)."""
+    root = Path(package_root) / "fullwave"
+    write_mat(root / "utils" / "bins" / "database" / DB_NAME)          # RelaxationParametersGenerator's own default
+    return write_mat(root / "solver" / "bins" / "database" / DB_NAME)
 
 
 def lookup_table():

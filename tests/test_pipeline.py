@@ -46,7 +46,8 @@ def spec_and_problem(user_shape, *, n_pml, n_trans, nT, modT, seed, lut=False, f
     # a plane source near the low-x face, point sources on block edges, a few in the rim; sensors and air everywhere
     ys, zs = np.meshgrid(np.arange(nb, ext[1] - nb), np.arange(nb, ext[2] - nb), indexing="ij")
     plane = np.stack([np.full(ys.size, nb), ys.ravel(), zs.ravel()], axis=1).astype(np.int32)
-    icc = np.concatenate([plane, pts(12, planes=near), pts(3, lo=0, planes=[1, 5, ext[0] - 3])])
+    # (no point source on the plane source's own plane: two sources on one cell are a write race in any engine)
+    icc = np.concatenate([plane, pts(12, planes=[x for x in near if x != nb]), pts(3, lo=0, planes=[1, 5, ext[0] - 3])])
     nTic = min(nT, 30)
     pulse = synthetic.tone_burst(nTic, dt, mc.F0).astype(np.float32)
     icmat = np.concatenate([np.repeat(pulse[None], len(plane), 0), 0.3 * np.repeat(pulse[None], len(icc) - len(plane), 0)])
@@ -80,7 +81,7 @@ def test_pipelined_run_is_bit_identical_to_sequential(monkeypatch, skew):
         monkeypatch.setenv("FW25_SKEW_STEPS", str(nT) if skew == "all" else skew)
     got, stats = mapgen.run_medium(spec, pb)
     np.testing.assert_array_equal(got, want)
-    expect = {"auto": min(nT, 5), "all": nT}.get(skew, int(skew) if skew.isdigit() else None)
+    expect = {"auto": 2, "all": nT}.get(skew, int(skew) if skew.isdigit() else None)      # auto: max(2, 5 blocks // 3)
     assert stats["skewed_steps"] == expect
     assert stats["point_updates"] == pb.n_points * nT
 
@@ -94,7 +95,7 @@ def test_pipelined_run_lookup_and_float32_inputs(monkeypatch, lut, f32):
     want, _ = sequential(spec, pb)
     got, stats = mapgen.run_medium(spec, pb)
     np.testing.assert_array_equal(got, want)
-    assert stats["skewed_steps"] == 4 and np.abs(want).max() > 0
+    assert stats["skewed_steps"] == 2 and np.abs(want).max() > 0
 
 
 def test_streamed_maps_equal_one_shot_maps(monkeypatch):

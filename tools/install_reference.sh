@@ -38,6 +38,14 @@ include = ["fullwave*"]
 TOML
 python -m pip install --no-index --no-build-isolation --no-deps --find-links /opt/wheelhouse \
     --target "$REPO/baseline/_ref" "$TMP" 2>&1 | tail -3
+# the shipped example scripts (BASELINE.json configs 1-4) are not part of the wheel: staged next to the package so that
+# bench.py --config examples can run them verbatim on the GPU box (baseline/_ref is git-ignored; nothing is copied
+# into the repository's history)
+rm -rf "$REPO/baseline/_ref/examples"
+tar -C "$SRC" --exclude='*.ipynb' -cf - examples | tar -C "$REPO/baseline/_ref" -xf -
+# the relaxation-parameter database is missing from the reference checkout (.MISSING_LARGE_BLOBS): a stand-in with the
+# same schema goes where fullwave.Medium looks for it -- into baseline/_ref ONLY (fullwave25_b200/lut_standin.py)
+( cd "$REPO" && python -c "from fullwave25_b200 import lut_standin; print('stand-in LUT:', lut_standin.install_into('baseline/_ref'))" )
 # pip drops the executable bit of package data on some versions; the launcher needs it
 find "$REPO/baseline/_ref/fullwave/solver/bins" -type f -name 'fullwave2_*' -exec chmod +x {} +
 echo "installed: $(find "$REPO/baseline/_ref" -type f | wc -l) files, $(du -sh "$REPO/baseline/_ref" | cut -f1)"
