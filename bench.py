@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- 3D FDTD Gpoint-updates/s of the Fullwave 2.5 time-stepping engine on B200 (BASELINE.json).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--grid XxYxZ]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--grid XxYxZ] [--config synthetic|examples]
 
 Workload (BASELINE.json configs[4]): synthetic heterogeneous attenuating 3D medium,
 extended grid `--grid` PER GPU (default 800x1240x1240 = 1.23e9 points ~ 148 GB resident), x-slab sharded
@@ -9,12 +9,23 @@ over N GPUs (weak scaling: nX = N * 800), 3-layer plane source, 1024 point senso
 A "step" is one time step (inject -> fd_u -> fd_p -> record) over the whole grid.  Every array is far larger
 than L2 (126 MB), so no flush is needed between steps.
 
-Our arm: one process per GPU (torchrun for N > 1), libfw25.so kernels, NCCL halo exchange.  `value` is timed
-with CUDA events with the maps already resident in HBM; `e2e` runs the same job through the public API from
-pinned HOST buffers (upload + steps + sensor read-back in the timed region).
-Reference arm (--impl reference): the reference's own shipped sm_100 CUDA executable (the reference has no
-CPU engine) driven through its Python launcher (`fullwave.solver.launcher.Launcher`, from baseline/_ref) on a
-bounded sample of the same workload (same medium recipe, smaller grid), rate by differencing two runs.
+Our arm: one process per GPU (torchrun for N > 1), libfw25.so kernels, NCCL halo exchange.
+  value        K steps timed with CUDA events, maps resident in HBM, max over ranks
+  roofline     the dominant sweep kernel against the measured HBM copy bandwidth (N = 1), traffic from the committed ncu capture
+  e2e          N = 1: the whole job through `fw25_run_medium` (C-ABI) from the USER-grid medium in pinned host memory --
+               allocation, host->device copies, map generation, K steps, frames back, free -- checked bit for bit against
+               the sequential path; `hostmaps_variant` (and N > 1): the 14 engine maps uploaded from pinned host memory
+  same_grid    our rate on the grid the reference arm runs (the largest it can hold), in the reference binary's own dcmap
+               mode, with the sha256 of the sensor frames: equal to the reference arm's `genout_sha256` = bit-identical
+  parity_n_vs_1 (N > 1) N ranks vs rank 0 alone on a mid-size grid with sources / sensors / air voxels ON the interfaces
+  halo         (N > 1) exposed halo-exchange time: the same steps with and without the transfers
+  strong       (N > 1) strong scaling: the ONE-GPU grid split over the N GPUs
+  cpu_baseline the oracle port on the host cores; host_setup_baseline: the reference's host-side map building at the
+               wave_3d example's size, with fw25_mapgen beside it
+Reference arm (--impl reference): the reference's own shipped sm_100 CUDA executable (it has no CPU engine) through its
+own `fullwave.solver.launcher.Launcher` (baseline/_ref), same workload recipe on the largest grid the reference can
+hold (560x1240x1240 per GPU on a 1- or 2-GPU box), timed per step from its progress prints (tools/bench_reference.py).
+--config examples: BASELINE.json configs 1-4, the reference's shipped example scripts verbatim on both engines.
 """
 
 from __future__ import annotations
@@ -116,11 +127,12 @@ def cpu_baseline(seconds: float = 12.0) -> dict:
 
 def host_setup_baseline() -> dict | None:
     """Host-side medium / relaxation setup of the REFERENCE (PMLBuilder.run + InputFileWriter stencil tables,
-    solver.py:693-743) timed on this box's cores on a bounded grid -- BASELINE.json asks for it beside the
-    engine numbers -- with the GPU map builder (fw25_mapgen) on the same grid next to it."""
+    solver.py:693-743) timed on this box's cores at BASELINE.json configs[3]'s size (120^3 user grid -> 280^3) --
+    BASELINE.json asks for it beside the engine numbers, with the core count -- and the GPU map builder
+    (fw25_mapgen) on the same grid next to it."""
     try:
         from tools import ref_objects
-        return ref_objects.time_host_setup((40, 64, 64), gpu=True)
+        return ref_objects.time_host_setup((120, 120, 120), gpu=True)    # the wave_3d example's user grid (config 4)
     except Exception as e:  # noqa: BLE001
         return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
 
@@ -551,6 +563,40 @@ def run_reference(args):
     bench_reference.run_reference(args, metric=METRIC, unit=UNIT, workload=WORKLOAD, medium=MEDIUM)
 
 
+def run_examples_config(args):
+    """--config examples: BASELINE.json configs 1-4, the reference's four shipped example set-ups run verbatim through
+    `fullwave.Solver.run` on the reference binary and on this engine (tools/run_examples.py).  One JSON line."""
+    from tools import run_examples
+    names = args.examples.split(",") if args.examples else list(run_examples.EXAMPLES)
+    res = run_examples.run_all(names, tuple(args.example_engines.split(",")), args.duration_scale, log=lambda s: None)
+    by = {}
+    for r in res:
+        by.setdefault(r["example"], {})[r["engine"]] = {k: v for k, v in r.items() if k not in ("example", "engine")}
+    table = {}
+    for name, e in by.items():
+        ref, dev, host = e.get("reference", {}), e.get("fw25-device", {}), e.get("fw25-host", {})
+        table[name] = {
+            "extended_grid": ref.get("extended_grid") or dev.get("extended_grid"), "steps": ref.get("steps") or dev.get("steps"),
+            "sensors": ref.get("sensors") or dev.get("sensors"), "frames": ref.get("frames") or dev.get("frames"),
+            "engine_Gpts": {k: v.get("engine_Gpts") for k, v in e.items()},
+            "roofline_frac": {k: v.get("roofline_frac") for k, v in e.items() if k != "reference"},
+            "solver_run_s": {k: v.get("solver_run_s") for k, v in e.items()},
+            "solver_init_s": {k: v.get("solver_init_s") for k, v in e.items()},
+            "vs_reference": {k: v.get("vs_reference") for k, v in e.items() if k != "reference"},
+            "errors": {k: v["error"] for k, v in e.items() if "error" in v} or None,
+        }
+    vals = [t["engine_Gpts"].get("fw25-device") or t["engine_Gpts"].get("fw25-host") for t in table.values()]
+    vals = [v for v in vals if v]
+    print(json.dumps({
+        "metric": "FDTD Gpoint-updates/s (engine time loop), BASELINE.json configs 1-4", "unit": UNIT,
+        "value": float(np.exp(np.mean(np.log(vals)))) if vals else None, "value_is": "geometric mean over the examples",
+        "n_gpus": 1, "higher_is_better": True, "dtype": "f32", "data": "the reference's example scripts, verbatim",
+        "config": {"workload": "examples/{simple_plane_wave, linear_transducer, convex_transducer, wave_3d} (BASELINE.json "
+                               "configs[0..3])", "duration_scale": args.duration_scale,
+                   "relaxation_table": "stand-in (fullwave25_b200/lut_standin.py)", "harness": "tools/run_examples.py"},
+        "examples": table}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -561,6 +607,11 @@ def main():
     ap.add_argument("--ref-planes", type=int, default=None,
                     help="x planes per GPU of the reference arm's grid (default: the largest the reference can hold here)")
     ap.add_argument("--no-ref-crosscheck", action="store_true")
+    ap.add_argument("--config", default="synthetic", choices=["synthetic", "examples"],
+                    help="synthetic: BASELINE.json configs[4] (default); examples: configs[0..3], the shipped example scripts")
+    ap.add_argument("--examples", default="", help="comma-separated subset for --config examples")
+    ap.add_argument("--example-engines", default="reference,fw25-host,fw25-device")
+    ap.add_argument("--duration-scale", type=float, default=1.0, help="--config examples: scale every example's duration")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-e2e-check", action="store_true")
     ap.add_argument("--no-strong", action="store_true")
@@ -569,7 +620,9 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
-    if args.impl == "reference":
+    if args.config == "examples":
+        run_examples_config(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

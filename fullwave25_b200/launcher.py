@@ -35,6 +35,7 @@ class SimulationError(Exception):
     that catches the reference's exception keeps working."""
 
 
+last_run_stats: dict | None = None   # engine statistics of the most recent run_solver call (fw25_stats + extras)
 _raise_cls = SimulationError          # install() swaps in a subclass of both error types
 _reference_launcher_cls = None        # the reference's own Launcher, kept by install() for the runs this engine does not cover
 
@@ -403,6 +404,11 @@ def _run_solver_device_maps(solver, sensor, out_box, device: int, session: Sessi
     return genout, stats, pb
 
 
+def _remember(stats: dict) -> None:
+    global last_run_stats
+    last_run_stats = dict(stats)
+
+
 def run_solver(solver, *, record_whole_domain: bool = False, sampling_modulus_time_whole_domain: int = 1,
                cuda_device_id=None, return_stats: bool = False, session: Session | None = None,
                maps: str = "host"):
@@ -424,6 +430,7 @@ def run_solver(solver, *, record_whole_domain: bool = False, sampling_modulus_ti
         except (engine.EngineError, ValueError) as e:
             raise _sim_error(str(e)) from e
         result = genout.reshape(-1, pb.ncoordsout).T
+        _remember(stats)
         return (result, stats) if return_stats else result
     if session is not None and session.eng is not None:      # next transmit event: only the sources change
         src = lean_lists(solver.pml_builder)[0]
@@ -449,6 +456,7 @@ def run_solver(solver, *, record_whole_domain: bool = False, sampling_modulus_ti
         except (engine.EngineError, ValueError) as e:
             raise _sim_error(str(e)) from e
         result = genout.reshape(-1, session.eng.pb.ncoordsout).T
+        _remember(stats)
         return (result, stats) if return_stats else result
     extended_medium = solver.pml_builder.run(use_pml=solver.use_pml)
     sensor, out_box = _sensor_and_box(solver, record_whole_domain, sampling_modulus_time_whole_domain)
@@ -465,4 +473,5 @@ def run_solver(solver, *, record_whole_domain: bool = False, sampling_modulus_ti
     except (engine.EngineError, ValueError) as e:
         raise _sim_error(str(e)) from e
     result = genout.reshape(-1, pb.ncoordsout).T          # solver.py:600-618
+    _remember(stats)
     return (result, stats) if return_stats else result
