@@ -33,5 +33,23 @@ CASES_ANISO = {
 CASES.update(CASES_ANISO)
 
 
+# BASELINE.json-sized grids (configs[3]: 280^3 = examples/wave_3d; configs[2]: 1457 x 2178 = examples/convex_transducer)
+# with the boundary layer the reference's Solver uses (36 + 36 + 8 cells): a few hundred steps, 400 sensors in the part
+# of the domain the pulse reaches.  Goldens: tests/golden/ref_big{3d,2d}.npz (reference sm_100 binaries on a B200).
+CASES_BIG = {
+    "big3d": dict(shape=(280, 280, 280), nT=320, modT=4, seed=51, n_pml=36, n_trans=36, block=20, n_sensors=6000, n_air=300),
+    "big2d": dict(shape=(1457, 2178), nT=480, modT=4, seed=52, n_pml=36, n_trans=36, block=30, n_sensors=12000, n_air=60),
+}
+
+
 def make(name):
+    if name in CASES_BIG:
+        import numpy as np
+        kw = dict(CASES_BIG[name])
+        pb = synthetic.make_problem(**kw)
+        nb = 8 + kw["n_pml"] + kw["n_trans"]
+        reach = nb + int(kw["nT"] * 0.2) + 12                 # cfl 0.2: the pulse front after nT steps
+        near = pb.outc[pb.outc[:, 0] < reach]
+        pb.outc = np.ascontiguousarray(near[:: max(1, len(near) // 400)][:400])
+        return pb.normalise()
     return synthetic.make_problem(**CASES[name])

@@ -268,3 +268,15 @@ def test_fused_2d_step_equals_separate_kernels(built_lib, name, sensors, monkeyp
     half.nT, half.outc, half.icczero = pb.nT, pb.outc, pb.icczero
     half.icc, half.icmat = pb.icc[::2], pb.icmat[::2] * np.float32(0.5)
     np.testing.assert_array_equal(second, oracle.run(half))
+
+
+@pytest.mark.parametrize("name", ["big2d", "big3d"])
+def test_baseline_size_grids_match_reference_goldens(built_lib, name):
+    """BASELINE.json configs[2] / configs[3] grids (1457 x 2178, 280^3) with the reference Solver's boundary layer:
+    the engine's default kernels (TMA-tiled 2D sweeps / warp-specialised 3D sweeps, graph replay as configured) equal
+    the reference's sm_100 binaries bit for bit -- tests/golden/ref_big{2d,3d}.npz, tools/make_ref_golden.py."""
+    from tests.test_oracle_golden import load_golden
+    want = load_golden(name)
+    got, stats = engine.run(cases.make(name))
+    assert got.shape == want.shape and np.abs(want).max() > 1.0
+    np.testing.assert_array_equal(got, want)

@@ -101,7 +101,8 @@ def main() -> None:
             continue
         head = "\n".join(l for l in log.splitlines() if "Progress" not in l)[:4000]
         (out / f"ref_{name}{suffix}.log").write_text(head)
-        np.savez_compressed(out / f"ref_{name}{suffix}.npz", genout=g, case=json.dumps(cases.CASES[name]),
+        np.savez_compressed(out / f"ref_{name}{suffix}.npz", genout=g,
+                            case=json.dumps(cases.CASES.get(name) or cases.CASES_BIG[name]),
                             devices=devices)
         rec = {"frames": int(g.shape[0]), "sensors": int(g.shape[1]), "wall_s": round(dt, 3),
                "finite": bool(np.isfinite(g).all()), "absmax": float(np.abs(g).max()) if g.size else 0.0}
