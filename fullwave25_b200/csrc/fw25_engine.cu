@@ -335,6 +335,13 @@ void Engine::init(const fw25_problem &pb, const fw25_slab *slab, int dev) {
       if (!ws) fail(2, "warp-specialised sweep setup failed: " + perr);
     }
   }
+  if (aniso && ws_supported(ndim, G)) {     // truly per-axis maps: the warp-specialised sweeps with 10 more tiles per plane
+    std::string perr;
+    std::vector<float> hd((size_t)18 * pb.ndmap);
+    memcpy(hd.data(), pb.dmap, hd.size() * 4);
+    ws = ws_plan_create(F, G, hd.data(), stream, &perr, /*aniso=*/true);
+    if (!ws) fail(2, "warp-specialised anisotropic sweep setup failed: " + perr);
+  }
 
   if (!aniso && sweeps2d_supported(ndim, G)) {
     std::string perr;

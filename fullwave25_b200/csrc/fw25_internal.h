@@ -39,7 +39,9 @@ int launch_sweep_p_tiled(const TiledPlan *pl, const Fields &F, const Geom &G, in
 // warp-specialised all-TMA sweeps (3D): fw25_sweeps_ws.cu
 struct WsPlan;
 bool ws_supported(int ndim, const Geom &G);
-WsPlan *ws_plan_create(const Fields &F, const Geom &G, const float *host_dmap, cudaStream_t st, std::string *err);
+// aniso: the anisotropic-relaxation family -- per-axis kappa / a / b tiles (Fields::kv .. bp), smaller tiles
+WsPlan *ws_plan_create(const Fields &F, const Geom &G, const float *host_dmap, cudaStream_t st, std::string *err,
+                       bool aniso = false);
 void ws_plan_destroy(WsPlan *pl);
 // push != nullptr: fused halo exchange -- the launch also stores its results into the neighbour's ghost planes
 int launch_sweep_u_ws(const WsPlan *pl, const Fields &F, const Geom &G, int a_lo, int a_hi, cudaStream_t st,

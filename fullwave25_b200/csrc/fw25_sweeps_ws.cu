@@ -61,6 +61,14 @@ enum : int {
 };
 constexpr int NPW_U = MU_END - MU_PNEW;   // 18 point-wise tiles per plane in fd_u
 constexpr int NPW_P = MP_END - MP_UNEW;   // 16 in fd_p
+// Anisotropic-relaxation family (one kappa / a / b map per axis, input_file_writer.py:592-620): the per-sweep slots
+// above hold axis A (x); axes B and C add 5 point-wise tiles each (kappa, a1, b1, a2, b2) behind the isotropic ones.
+constexpr int NX_ANISO = 10;
+constexpr int MXU = MP_END, MXP = MXU + NX_ANISO, M_END_ANISO = MXP + NX_ANISO;   // tensor-map slots of the extras
+enum : int { X_KAPPA = 0, X_A1, X_B1, X_A2, X_B2 };
+__host__ __device__ constexpr int npw_u(bool aniso) { return NPW_U + (aniso ? NX_ANISO : 0); }
+__host__ __device__ constexpr int npw_p(bool aniso) { return NPW_P + (aniso ? NX_ANISO : 0); }
+__host__ __device__ constexpr int xslot(int npw_iso, int axis, int which) { return npw_iso + (axis - 1) * 5 + which; }   // axis 1 (B), 2 (C)
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
@@ -84,21 +92,21 @@ __device__ __forceinline__ void tile_of_block(int strip, int &bx, int &by) {
   bx = s * strip + r - by * w;
 }
 
-template <int TY>
+template <int TY, int NPW>
 struct alignas(128) SmemU {
   float halo[NH][TY + 2 * M][TZ + 2 * M];
-  float pw[NP][NPW_U][TY][TZ];
+  float pw[NP][NPW][TY][TZ];
   uint64_t full_h[NH], empty_h[NH], full_p[NP], empty_p[NP];
 };
 
-template <int TY>
+template <int TY, int NPW>
 struct alignas(128) SmemP {
   struct alignas(128) Halo {
     alignas(128) float u[TY + 2][TZ + 8];
     alignas(128) float v[TY + 2 * M][TZ + 8];
     alignas(128) float w[TY + 2][TZ + 2 * M];
   } halo[NH];
-  float pw[NP][NPW_P][TY][TZ];
+  float pw[NP][NPW][TY][TZ];
   uint64_t full_h[NH], empty_h[NH], full_p[NP], empty_p[NP];
 };
 
@@ -106,14 +114,15 @@ struct alignas(128) SmemP {
 // PUSH: the launch covers the planes next to an x-slab interface and also stores its results into the neighbour
 // GPU's ghost planes through a peer-mapped pointer (NVLink): the halo exchange is part of the sweep, tile by
 // tile, instead of a copy after it (u: every plane of the launch; v, w: only the plane the cross terms read).
-template <int TY, int MINB, bool PUSH>
+template <int TY, int MINB, bool PUSH, bool ANISO>
 __global__ void __launch_bounds__((TY + 1) * TZ, MINB)
     k_sweep_u_ws(const CUtensorMap *__restrict__ maps, const Fields F, const Geom G,
                  const StencilTab *__restrict__ tab, int a_lo, int a_hi, int Lx, int hint, const HaloPush push) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  SmemU<TY> &S = *reinterpret_cast<SmemU<TY> *>(smem_raw);
+  constexpr int NPW = npw_u(ANISO);
+  SmemU<TY, NPW> &S = *reinterpret_cast<SmemU<TY, NPW> *>(smem_raw);
   constexpr int HY = TY + 2 * M, HZ = TZ + 2 * M;
-  constexpr uint32_t HALO_BYTES = HY * HZ * 4, PW_BYTES = NPW_U * TY * TZ * 4;
+  constexpr uint32_t HALO_BYTES = HY * HZ * 4, PW_BYTES = NPW * TY * TZ * 4;
 
   const int tz = threadIdx.x, ty = threadIdx.y;
   int bx, by;
@@ -158,12 +167,13 @@ __global__ void __launch_bounds__((TY + 1) * TZ, MINB)
           else tma_load_3d(&S.pw[s][0][0][0], &maps[MU_PNEW], z0, y0, P + M, &S.full_p[s]);
           if (hint & 1) {
 #pragma unroll
-            for (int a = 1; a < NPW_U; ++a)
-              tma_load_3d_hint(&S.pw[s][a][0][0], &maps[MU_PNEW + a], z0, y0, P, &S.full_p[s], pol_stream);
+            for (int a = 1; a < NPW; ++a)
+              tma_load_3d_hint(&S.pw[s][a][0][0], &maps[a < NPW_U ? MU_PNEW + a : MXU + a - NPW_U], z0, y0, P,
+                               &S.full_p[s], pol_stream);
           } else {
 #pragma unroll
-            for (int a = 1; a < NPW_U; ++a)
-              tma_load_3d(&S.pw[s][a][0][0], &maps[MU_PNEW + a], z0, y0, P, &S.full_p[s]);
+            for (int a = 1; a < NPW; ++a)
+              tma_load_3d(&S.pw[s][a][0][0], &maps[a < NPW_U ? MU_PNEW + a : MXU + a - NPW_U], z0, y0, P, &S.full_p[s]);
           }
         }
       }
@@ -250,15 +260,23 @@ FW25_UNROLL_X(FW25_WS_UNROLL)
       const float a1 = W[MU_A1 - MU_PNEW][ty][tz], b1 = W[MU_B1 - MU_PNEW][ty][tz];
       const float a2 = W[MU_A2 - MU_PNEW][ty][tz], b2 = W[MU_B2 - MU_PNEW][ty][tz];
       const float s = div_(div_(G.dT, rho), fma_(rcp_(Kc), pcen, 1.0f));
+      float kxB = kx, a1B = a1, b1B = b1, a2B = a2, b2B = b2, kxC = kx, a1C = a1, b1C = b1, a2C = a2, b2C = b2;
+      if constexpr (ANISO) {
+        kxB = W[xslot(NPW_U, 1, X_KAPPA)][ty][tz]; kxC = W[xslot(NPW_U, 2, X_KAPPA)][ty][tz];
+        a1B = W[xslot(NPW_U, 1, X_A1)][ty][tz]; b1B = W[xslot(NPW_U, 1, X_B1)][ty][tz];
+        a2B = W[xslot(NPW_U, 1, X_A2)][ty][tz]; b2B = W[xslot(NPW_U, 1, X_B2)][ty][tz];
+        a1C = W[xslot(NPW_U, 2, X_A1)][ty][tz]; b1C = W[xslot(NPW_U, 2, X_B1)][ty][tz];
+        a2C = W[xslot(NPW_U, 2, X_A2)][ty][tz]; b2C = W[xslot(NPW_U, 2, X_B2)][ty][tz];
+      }
       const float m00 = fma_(b1, W[MU_M00 - MU_PNEW][ty][tz], mul_(gA, a1));
       const float m01 = fma_(b2, W[MU_M01 - MU_PNEW][ty][tz], mul_(gA, a2));
-      const float m10 = fma_(b1, W[MU_M10 - MU_PNEW][ty][tz], mul_(gB, a1));
-      const float m11 = fma_(b2, W[MU_M11 - MU_PNEW][ty][tz], mul_(gB, a2));
-      const float m20 = fma_(b1, W[MU_M20 - MU_PNEW][ty][tz], mul_(gC, a1));
-      const float m21 = fma_(b2, W[MU_M21 - MU_PNEW][ty][tz], mul_(gC, a2));
+      const float m10 = fma_(b1B, W[MU_M10 - MU_PNEW][ty][tz], mul_(gB, a1B));
+      const float m11 = fma_(b2B, W[MU_M11 - MU_PNEW][ty][tz], mul_(gB, a2B));
+      const float m20 = fma_(b1C, W[MU_M20 - MU_PNEW][ty][tz], mul_(gC, a1C));
+      const float m21 = fma_(b2C, W[MU_M21 - MU_PNEW][ty][tz], mul_(gC, a2C));
       const float q0 = fma_(-s, add_(add_(div_(gA, kx), m00), m01), W[MU_Q0 - MU_PNEW][ty][tz]);
-      const float q1 = fma_(-s, add_(add_(div_(gB, kx), m10), m11), W[MU_Q1 - MU_PNEW][ty][tz]);
-      const float q2 = fma_(-s, add_(add_(div_(gC, kx), m20), m21), W[MU_Q2 - MU_PNEW][ty][tz]);
+      const float q1 = fma_(-s, add_(add_(div_(gB, kxB), m10), m11), W[MU_Q1 - MU_PNEW][ty][tz]);
+      const float q2 = fma_(-s, add_(add_(div_(gC, kxC), m20), m21), W[MU_Q2 - MU_PNEW][ty][tz]);
       __stcs(F.psi[0][0] + gi, m00); __stcs(F.psi[0][1] + gi, m01);
       __stcs(F.psi[1][0] + gi, m10); __stcs(F.psi[1][1] + gi, m11);
       __stcs(F.psi[2][0] + gi, m20); __stcs(F.psi[2][1] + gi, m21);
@@ -279,14 +297,15 @@ FW25_UNROLL_X(FW25_WS_UNROLL)
 }
 
 // ------------------------------------------------------------------------------------------ fd_p
-template <int TY, int MINB, bool PUSH>
+template <int TY, int MINB, bool PUSH, bool ANISO>
 __global__ void __launch_bounds__((TY + 1) * TZ, MINB)
     k_sweep_p_ws(const CUtensorMap *__restrict__ maps, const Fields F, const Geom G,
                  const StencilTab *__restrict__ tab, int a_lo, int a_hi, int Lx, int hint, const HaloPush push) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  SmemP<TY> &S = *reinterpret_cast<SmemP<TY> *>(smem_raw);
+  constexpr int NPW = npw_p(ANISO);
+  SmemP<TY, NPW> &S = *reinterpret_cast<SmemP<TY, NPW> *>(smem_raw);
   constexpr uint32_t U_BYTES = (TY + 2) * (TZ + 8) * 4, V_BYTES = (TY + 2 * M) * (TZ + 8) * 4,
-                     W_BYTES = (TY + 2) * (TZ + 2 * M) * 4, PW_BYTES = NPW_P * TY * TZ * 4;
+                     W_BYTES = (TY + 2) * (TZ + 2 * M) * 4, PW_BYTES = NPW * TY * TZ * 4;
 
   const int tz = threadIdx.x, ty = threadIdx.y;
   int bx, by;
@@ -335,12 +354,13 @@ __global__ void __launch_bounds__((TY + 1) * TZ, MINB)
           else tma_load_3d(&S.pw[s][0][0][0], &maps[MP_UNEW], z0, y0, P + M - 1, &S.full_p[s]);   // u[x+7]
           if (hint & 1) {
 #pragma unroll
-            for (int a = 1; a < NPW_P; ++a)
-              tma_load_3d_hint(&S.pw[s][a][0][0], &maps[MP_UNEW + a], z0, y0, P, &S.full_p[s], pol_stream);
+            for (int a = 1; a < NPW; ++a)
+              tma_load_3d_hint(&S.pw[s][a][0][0], &maps[a < NPW_P ? MP_UNEW + a : MXP + a - NPW_P], z0, y0, P,
+                               &S.full_p[s], pol_stream);
           } else {
 #pragma unroll
-            for (int a = 1; a < NPW_P; ++a)
-              tma_load_3d(&S.pw[s][a][0][0], &maps[MP_UNEW + a], z0, y0, P, &S.full_p[s]);
+            for (int a = 1; a < NPW; ++a)
+              tma_load_3d(&S.pw[s][a][0][0], &maps[a < NPW_P ? MP_UNEW + a : MXP + a - NPW_P], z0, y0, P, &S.full_p[s]);
           }
         }
       }
@@ -374,9 +394,9 @@ FW25_UNROLL_X(FW25_WS_UNROLL)
     mbar_wait(&S.full_p[n & (NP - 1)], (n / NP) & 1);
 
     if (act) {
-      const typename SmemP<TY>::Halo &Sm = S.halo[n & (NH - 1)];
-      const typename SmemP<TY>::Halo &S0 = S.halo[(n + 1) & (NH - 1)];
-      const typename SmemP<TY>::Halo &S1 = S.halo[(n + 2) & (NH - 1)];
+      const typename SmemP<TY, NPW>::Halo &Sm = S.halo[n & (NH - 1)];
+      const typename SmemP<TY, NPW>::Halo &S0 = S.halo[(n + 1) & (NH - 1)];
+      const typename SmemP<TY, NPW>::Halo &S1 = S.halo[(n + 2) & (NH - 1)];
       const float(*W)[TY][TZ] = S.pw[n & (NP - 1)];
       uc[15] = W[0][ty][tz];
       const int ci = __float_as_int(W[MP_DC - MP_UNEW][ty][tz]);
@@ -416,14 +436,22 @@ FW25_UNROLL_X(FW25_WS_UNROLL)
       const float a1 = W[MP_A1 - MP_UNEW][ty][tz], b1 = W[MP_B1 - MP_UNEW][ty][tz];
       const float a2 = W[MP_A2 - MP_UNEW][ty][tz], b2 = W[MP_B2 - MP_UNEW][ty][tz];
       const float pc = W[MP_P - MP_UNEW][ty][tz];
+      float kuB = ku, a1B = a1, b1B = b1, a2B = a2, b2B = b2, kuC = ku, a1C = a1, b1C = b1, a2C = a2, b2C = b2;
+      if constexpr (ANISO) {
+        kuB = W[xslot(NPW_P, 1, X_KAPPA)][ty][tz]; kuC = W[xslot(NPW_P, 2, X_KAPPA)][ty][tz];
+        a1B = W[xslot(NPW_P, 1, X_A1)][ty][tz]; b1B = W[xslot(NPW_P, 1, X_B1)][ty][tz];
+        a2B = W[xslot(NPW_P, 1, X_A2)][ty][tz]; b2B = W[xslot(NPW_P, 1, X_B2)][ty][tz];
+        a1C = W[xslot(NPW_P, 2, X_A1)][ty][tz]; b1C = W[xslot(NPW_P, 2, X_B1)][ty][tz];
+        a2C = W[xslot(NPW_P, 2, X_A2)][ty][tz]; b2C = W[xslot(NPW_P, 2, X_B2)][ty][tz];
+      }
       const float f00 = fma_(b1, W[MP_F00 - MP_UNEW][ty][tz], mul_(hA, a1));
       const float f01 = fma_(b2, W[MP_F01 - MP_UNEW][ty][tz], mul_(hA, a2));
-      const float f10 = fma_(b1, W[MP_F10 - MP_UNEW][ty][tz], mul_(hB, a1));
-      const float f11 = fma_(b2, W[MP_F11 - MP_UNEW][ty][tz], mul_(hB, a2));
-      const float f20 = fma_(b1, W[MP_F20 - MP_UNEW][ty][tz], mul_(hC, a1));
-      const float f21 = fma_(b2, W[MP_F21 - MP_UNEW][ty][tz], mul_(hC, a2));
-      float Ssum = add_(div_(hA, ku), div_(hB, ku));      // PTX L1290-1305
-      Ssum = add_(div_(hC, ku), Ssum);
+      const float f10 = fma_(b1B, W[MP_F10 - MP_UNEW][ty][tz], mul_(hB, a1B));
+      const float f11 = fma_(b2B, W[MP_F11 - MP_UNEW][ty][tz], mul_(hB, a2B));
+      const float f20 = fma_(b1C, W[MP_F20 - MP_UNEW][ty][tz], mul_(hC, a1C));
+      const float f21 = fma_(b2C, W[MP_F21 - MP_UNEW][ty][tz], mul_(hC, a2C));
+      float Ssum = add_(div_(hA, ku), div_(hB, kuB));      // PTX L1290-1305
+      Ssum = add_(div_(hC, kuC), Ssum);
       Ssum = add_(f00, Ssum); Ssum = add_(f01, Ssum); Ssum = add_(f10, Ssum); Ssum = add_(f11, Ssum);
       Ssum = add_(f20, Ssum); Ssum = add_(f21, Ssum);
       const float At = mul_(mul_(G.dT, Kc), Ssum);
@@ -486,6 +514,17 @@ bool tmap3d(CUtensorMap *m, const void *base, const Geom &G, int box_c, int box_
 
 constexpr int TY_WS = FW25_WS_TY;
 constexpr int MINB_WS = FW25_WS_MINB;
+// Anisotropic family: 28 (fd_u) / 26 (fd_p) point-wise tiles per plane.  Tile rows chosen so that two CTAs still fit
+// one SM's 227 KB of shared memory: fd_u 12 rows (107.6 KB), fd_p 10 rows (100.1 KB).
+#ifndef FW25_WS_TY_AU
+#define FW25_WS_TY_AU 12
+#endif
+#ifndef FW25_WS_TY_AP
+#define FW25_WS_TY_AP 10
+#endif
+constexpr int TY_AU = FW25_WS_TY_AU, TY_AP = FW25_WS_TY_AP;
+static_assert(sizeof(SmemU<TY_AU, npw_u(true)>) * 2 + 2048 <= 227 * 1024, "anisotropic fd_u: two CTAs per SM");
+static_assert(sizeof(SmemP<TY_AP, npw_p(true)>) * 2 + 2048 <= 227 * 1024, "anisotropic fd_p: two CTAs per SM");
 
 // bit 0: point-wise tiles are loaded with an L2 evict-first policy.  Helps long chunks, costs ~2 % at the default chunk
 //        length (profiles/sweep_lx_r01.txt): off.
@@ -520,8 +559,9 @@ int pick_chunk_ws(const Geom &G, int planes) {
 }  // namespace
 
 struct WsPlan {
-  CUtensorMap *maps = nullptr;   // device array [MP_END]
+  CUtensorMap *maps = nullptr;   // device array [MP_END], anisotropic: [M_END_ANISO]
   StencilTab *tab = nullptr;
+  bool aniso = false;
 };
 
 bool ws_supported(int ndim, const Geom &G) {
@@ -530,26 +570,51 @@ bool ws_supported(int ndim, const Geom &G) {
          encode_fn_ws() != nullptr;
 }
 
-WsPlan *ws_plan_create(const Fields &F, const Geom &G, const float *host_dmap, cudaStream_t st, std::string *err) {
-  std::vector<CUtensorMap> h(MP_END);
+namespace {
+template <class K>
+bool allow_smem(K kernel, size_t bytes) {
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) == cudaSuccess;
+}
+}  // namespace
+
+WsPlan *ws_plan_create(const Fields &F, const Geom &G, const float *host_dmap, cudaStream_t st, std::string *err,
+                       bool aniso) {
+  const int n_maps = aniso ? M_END_ANISO : MP_END;
+  const int ty_u = aniso ? TY_AU : TY_WS, ty_p = aniso ? TY_AP : TY_WS;
+  std::vector<CUtensorMap> h(n_maps);
   bool ok = true;
-  auto centre = [&](int slot, const void *base) { ok = ok && tmap3d(&h[slot], base, G, TZ, TY_WS, err); };
-  ok = ok && tmap3d(&h[MU_PHALO], F.p, G, TZ + 2 * M, TY_WS + 2 * M, err);
-  centre(MU_PNEW, F.p); centre(MU_DC, F.dcmap); centre(MU_RHO, F.rho); centre(MU_K, F.K); centre(MU_KX, F.kappax);
-  centre(MU_A1, F.ax1); centre(MU_B1, F.bx1); centre(MU_A2, F.ax2); centre(MU_B2, F.bx2);
-  centre(MU_Q0, F.q[0]); centre(MU_Q1, F.q[1]); centre(MU_Q2, F.q[2]);
-  centre(MU_M00, F.psi[0][0]); centre(MU_M01, F.psi[0][1]); centre(MU_M10, F.psi[1][0]);
-  centre(MU_M11, F.psi[1][1]); centre(MU_M20, F.psi[2][0]); centre(MU_M21, F.psi[2][1]);
-  ok = ok && tmap3d(&h[MP_UHALO], F.q[0], G, TZ + 8, TY_WS + 2, err) &&
-       tmap3d(&h[MP_VHALO], F.q[1], G, TZ + 8, TY_WS + 2 * M, err) &&
-       tmap3d(&h[MP_WHALO], F.q[2], G, TZ + 2 * M, TY_WS + 2, err);
-  centre(MP_UNEW, F.q[0]); centre(MP_DC, F.dcmap); centre(MP_K, F.K); centre(MP_BETA, F.beta); centre(MP_KU, F.kappau);
-  centre(MP_A1, F.au1); centre(MP_B1, F.bu1); centre(MP_A2, F.au2); centre(MP_B2, F.bu2); centre(MP_P, F.p);
-  centre(MP_F00, F.phi[0][0]); centre(MP_F01, F.phi[0][1]); centre(MP_F10, F.phi[1][0]);
-  centre(MP_F11, F.phi[1][1]); centre(MP_F20, F.phi[2][0]); centre(MP_F21, F.phi[2][1]);
+  auto centre_u = [&](int slot, const void *base) { ok = ok && tmap3d(&h[slot], base, G, TZ, ty_u, err); };
+  auto centre_p = [&](int slot, const void *base) { ok = ok && tmap3d(&h[slot], base, G, TZ, ty_p, err); };
+  ok = ok && tmap3d(&h[MU_PHALO], F.p, G, TZ + 2 * M, ty_u + 2 * M, err);
+  centre_u(MU_PNEW, F.p); centre_u(MU_DC, F.dcmap); centre_u(MU_RHO, F.rho); centre_u(MU_K, F.K);
+  centre_u(MU_KX, F.kv[0]); centre_u(MU_A1, F.av[0][0]); centre_u(MU_B1, F.bv[0][0]);
+  centre_u(MU_A2, F.av[0][1]); centre_u(MU_B2, F.bv[0][1]);
+  centre_u(MU_Q0, F.q[0]); centre_u(MU_Q1, F.q[1]); centre_u(MU_Q2, F.q[2]);
+  centre_u(MU_M00, F.psi[0][0]); centre_u(MU_M01, F.psi[0][1]); centre_u(MU_M10, F.psi[1][0]);
+  centre_u(MU_M11, F.psi[1][1]); centre_u(MU_M20, F.psi[2][0]); centre_u(MU_M21, F.psi[2][1]);
+  ok = ok && tmap3d(&h[MP_UHALO], F.q[0], G, TZ + 8, ty_p + 2, err) &&
+       tmap3d(&h[MP_VHALO], F.q[1], G, TZ + 8, ty_p + 2 * M, err) &&
+       tmap3d(&h[MP_WHALO], F.q[2], G, TZ + 2 * M, ty_p + 2, err);
+  centre_p(MP_UNEW, F.q[0]); centre_p(MP_DC, F.dcmap); centre_p(MP_K, F.K); centre_p(MP_BETA, F.beta);
+  centre_p(MP_KU, F.kp[0]); centre_p(MP_A1, F.ap[0][0]); centre_p(MP_B1, F.bp[0][0]);
+  centre_p(MP_A2, F.ap[0][1]); centre_p(MP_B2, F.bp[0][1]); centre_p(MP_P, F.p);
+  centre_p(MP_F00, F.phi[0][0]); centre_p(MP_F01, F.phi[0][1]); centre_p(MP_F10, F.phi[1][0]);
+  centre_p(MP_F11, F.phi[1][1]); centre_p(MP_F20, F.phi[2][0]); centre_p(MP_F21, F.phi[2][1]);
+  if (aniso) {
+    for (int ax = 1; ax <= 2; ++ax) {
+      const int u0 = MXU + (ax - 1) * 5, p0 = MXP + (ax - 1) * 5;
+      centre_u(u0 + X_KAPPA, F.kv[ax]);
+      centre_u(u0 + X_A1, F.av[ax][0]); centre_u(u0 + X_B1, F.bv[ax][0]);
+      centre_u(u0 + X_A2, F.av[ax][1]); centre_u(u0 + X_B2, F.bv[ax][1]);
+      centre_p(p0 + X_KAPPA, F.kp[ax]);
+      centre_p(p0 + X_A1, F.ap[ax][0]); centre_p(p0 + X_B1, F.bp[ax][0]);
+      centre_p(p0 + X_A2, F.ap[ax][1]); centre_p(p0 + X_B2, F.bp[ax][1]);
+    }
+  }
   if (!ok) return nullptr;
 
   auto *pl = new WsPlan();
+  pl->aniso = aniso;
   std::vector<StencilTab> t(G.ndmap);
   const int nd = G.ndmap;
   for (int c = 0; c < nd; ++c) {
@@ -558,20 +623,22 @@ WsPlan *ws_plan_create(const Fields &F, const Geom &G, const float *host_dmap, c
     t[c].d47 = make_float4(Dk(5), Dk(6), Dk(7), Dk(8));
     t[c].e = make_float4(host_dmap[(size_t)3 * nd + c], 0.f, 0.f, 0.f);
   }
-  cudaError_t e1 = cudaMalloc(&pl->maps, sizeof(CUtensorMap) * MP_END);
+  cudaError_t e1 = cudaMalloc(&pl->maps, sizeof(CUtensorMap) * n_maps);
   cudaError_t e2 = cudaMalloc(&pl->tab, sizeof(StencilTab) * nd);
+  bool attr;
+  if (aniso) {
+    constexpr size_t su = sizeof(SmemU<TY_AU, npw_u(true)>), sp = sizeof(SmemP<TY_AP, npw_p(true)>);
+    attr = allow_smem(k_sweep_u_ws<TY_AU, MINB_WS, false, true>, su) && allow_smem(k_sweep_u_ws<TY_AU, MINB_WS, true, true>, su) &&
+           allow_smem(k_sweep_p_ws<TY_AP, MINB_WS, false, true>, sp) && allow_smem(k_sweep_p_ws<TY_AP, MINB_WS, true, true>, sp);
+  } else {
+    constexpr size_t su = sizeof(SmemU<TY_WS, NPW_U>), sp = sizeof(SmemP<TY_WS, NPW_P>);
+    attr = allow_smem(k_sweep_u_ws<TY_WS, MINB_WS, false, false>, su) && allow_smem(k_sweep_u_ws<TY_WS, MINB_WS, true, false>, su) &&
+           allow_smem(k_sweep_p_ws<TY_WS, MINB_WS, false, false>, sp) && allow_smem(k_sweep_p_ws<TY_WS, MINB_WS, true, false>, sp);
+  }
   if (e1 != cudaSuccess || e2 != cudaSuccess ||
-      cudaMemcpyAsync(pl->maps, h.data(), sizeof(CUtensorMap) * MP_END, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+      cudaMemcpyAsync(pl->maps, h.data(), sizeof(CUtensorMap) * n_maps, cudaMemcpyHostToDevice, st) != cudaSuccess ||
       cudaMemcpyAsync(pl->tab, t.data(), sizeof(StencilTab) * nd, cudaMemcpyHostToDevice, st) != cudaSuccess ||
-      cudaStreamSynchronize(st) != cudaSuccess ||
-      cudaFuncSetAttribute(k_sweep_u_ws<TY_WS, MINB_WS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)sizeof(SmemU<TY_WS>)) != cudaSuccess ||
-      cudaFuncSetAttribute(k_sweep_p_ws<TY_WS, MINB_WS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)sizeof(SmemP<TY_WS>)) != cudaSuccess ||
-      cudaFuncSetAttribute(k_sweep_u_ws<TY_WS, MINB_WS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)sizeof(SmemU<TY_WS>)) != cudaSuccess ||
-      cudaFuncSetAttribute(k_sweep_p_ws<TY_WS, MINB_WS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)sizeof(SmemP<TY_WS>)) != cudaSuccess) {
+      cudaStreamSynchronize(st) != cudaSuccess || !attr) {
     *err = std::string("warp-specialised plan: ") + cudaGetErrorString(cudaGetLastError());
     if (pl->maps) cudaFree(pl->maps);
     if (pl->tab) cudaFree(pl->tab);
@@ -588,33 +655,46 @@ void ws_plan_destroy(WsPlan *pl) {
   delete pl;
 }
 
+namespace {
+template <int TY, bool ANISO>
+void launch_u(const WsPlan *pl, const Fields &F, const Geom &G, int a_lo, int a_hi, cudaStream_t st, const HaloPush *push) {
+  const int Lx = pick_chunk_ws(G, a_hi - a_lo);
+  constexpr size_t smem = sizeof(SmemU<TY, npw_u(ANISO)>);
+  dim3 blk(TZ, TY + 1, 1);
+  dim3 grd((G.nC - M + TZ - 1) / TZ, (G.nB - 2 * M + TY - 1) / TY, (a_hi - a_lo + Lx - 1) / Lx);
+  if (push)
+    k_sweep_u_ws<TY, MINB_WS, true, ANISO><<<grd, blk, smem, st>>>(pl->maps, F, G, pl->tab, a_lo, a_hi, Lx, ws_hint(), *push);
+  else
+    k_sweep_u_ws<TY, MINB_WS, false, ANISO><<<grd, blk, smem, st>>>(pl->maps, F, G, pl->tab, a_lo, a_hi, Lx, ws_hint(),
+                                                                    HaloPush{});
+}
+template <int TY, bool ANISO>
+void launch_p(const WsPlan *pl, const Fields &F, const Geom &G, int a_lo, int a_hi, cudaStream_t st, const HaloPush *push) {
+  const int Lx = pick_chunk_ws(G, a_hi - a_lo);
+  constexpr size_t smem = sizeof(SmemP<TY, npw_p(ANISO)>);
+  dim3 blk(TZ, TY + 1, 1);
+  dim3 grd((G.nC - M + TZ - 1) / TZ, (G.nB - 2 * M + TY - 1) / TY, (a_hi - a_lo + Lx - 1) / Lx);
+  if (push)
+    k_sweep_p_ws<TY, MINB_WS, true, ANISO><<<grd, blk, smem, st>>>(pl->maps, F, G, pl->tab, a_lo, a_hi, Lx, ws_hint(), *push);
+  else
+    k_sweep_p_ws<TY, MINB_WS, false, ANISO><<<grd, blk, smem, st>>>(pl->maps, F, G, pl->tab, a_lo, a_hi, Lx, ws_hint(),
+                                                                    HaloPush{});
+}
+}  // namespace
+
 int launch_sweep_u_ws(const WsPlan *pl, const Fields &F, const Geom &G, int a_lo, int a_hi, cudaStream_t st,
                       const HaloPush *push) {
   if (a_hi <= a_lo) return 0;
-  const int Lx = pick_chunk_ws(G, a_hi - a_lo);
-  dim3 blk(TZ, TY_WS + 1, 1);
-  dim3 grd((G.nC - M + TZ - 1) / TZ, (G.nB - 2 * M + TY_WS - 1) / TY_WS, (a_hi - a_lo + Lx - 1) / Lx);
-  if (push)
-    k_sweep_u_ws<TY_WS, MINB_WS, true><<<grd, blk, sizeof(SmemU<TY_WS>), st>>>(pl->maps, F, G, pl->tab, a_lo, a_hi, Lx,
-                                                                                ws_hint(), *push);
-  else
-    k_sweep_u_ws<TY_WS, MINB_WS, false><<<grd, blk, sizeof(SmemU<TY_WS>), st>>>(pl->maps, F, G, pl->tab, a_lo, a_hi, Lx,
-                                                                                 ws_hint(), HaloPush{});
+  if (pl->aniso) launch_u<TY_AU, true>(pl, F, G, a_lo, a_hi, st, push);
+  else launch_u<TY_WS, false>(pl, F, G, a_lo, a_hi, st, push);
   return 1;
 }
 
 int launch_sweep_p_ws(const WsPlan *pl, const Fields &F, const Geom &G, int a_lo, int a_hi, cudaStream_t st,
                       const HaloPush *push) {
   if (a_hi <= a_lo) return 0;
-  const int Lx = pick_chunk_ws(G, a_hi - a_lo);
-  dim3 blk(TZ, TY_WS + 1, 1);
-  dim3 grd((G.nC - M + TZ - 1) / TZ, (G.nB - 2 * M + TY_WS - 1) / TY_WS, (a_hi - a_lo + Lx - 1) / Lx);
-  if (push)
-    k_sweep_p_ws<TY_WS, MINB_WS, true><<<grd, blk, sizeof(SmemP<TY_WS>), st>>>(pl->maps, F, G, pl->tab, a_lo, a_hi, Lx,
-                                                                                ws_hint(), *push);
-  else
-    k_sweep_p_ws<TY_WS, MINB_WS, false><<<grd, blk, sizeof(SmemP<TY_WS>), st>>>(pl->maps, F, G, pl->tab, a_lo, a_hi, Lx,
-                                                                                 ws_hint(), HaloPush{});
+  if (pl->aniso) launch_p<TY_AP, true>(pl, F, G, a_lo, a_hi, st, push);
+  else launch_p<TY_WS, false>(pl, F, G, a_lo, a_hi, st, push);
   return 1;
 }
 

@@ -151,20 +151,24 @@ def marshal(pb: Problem, *, device_maps: dict | None = None, ext_state: dict | N
     if ext_state:
         s.ext_p, s.ext_u = ext_state.get("p"), ext_state.get("u")
         s.ext_v, s.ext_w = ext_state.get("v"), ext_state.get("w")
-    if pb.aniso is not None:
-        if device_maps is not None:
-            raise EngineError("device-resident maps are isotropic only")
+    dev_aniso = (device_maps or {}).get("aniso")
+    if pb.aniso is not None or dev_aniso:
+        # anisotropic file set: host arrays (pb.aniso) or, with device-resident maps, {stem: device address} under
+        # device_maps["aniso"] in the same [nX][nY][pitch] layout
+        if device_maps is not None and not dev_aniso:
+            raise EngineError("device-resident maps of an anisotropic problem need device_maps['aniso']")
+        addr = (lambda stem: int(dev_aniso[stem])) if dev_aniso else (lambda stem: pb.aniso[stem].ctypes.data)
         an = CAniso()
         vel = ("x", "y", "z")[: pb.ndim]
         prs = ("u", "w") if pb.ndim == 2 else ("u", "v", "w")
         for ax in range(pb.ndim):
-            an.kappa_vel[ax] = pb.aniso["kappa" + vel[ax]].ctypes.data
-            an.kappa_prs[ax] = pb.aniso["kappa" + prs[ax]].ctypes.data
+            an.kappa_vel[ax] = addr("kappa" + vel[ax])
+            an.kappa_prs[ax] = addr("kappa" + prs[ax])
             for nu in range(2):
-                an.a_vel[ax][nu] = pb.aniso[f"apml{vel[ax]}{nu + 1}"].ctypes.data
-                an.b_vel[ax][nu] = pb.aniso[f"bpml{vel[ax]}{nu + 1}"].ctypes.data
-                an.a_prs[ax][nu] = pb.aniso[f"apml{prs[ax]}{nu + 1}"].ctypes.data
-                an.b_prs[ax][nu] = pb.aniso[f"bpml{prs[ax]}{nu + 1}"].ctypes.data
+                an.a_vel[ax][nu] = addr(f"apml{vel[ax]}{nu + 1}")
+                an.b_vel[ax][nu] = addr(f"bpml{vel[ax]}{nu + 1}")
+                an.a_prs[ax][nu] = addr(f"apml{prs[ax]}{nu + 1}")
+                an.b_prs[ax][nu] = addr(f"bpml{prs[ax]}{nu + 1}")
         keep.append(an)
         s.aniso = C.pointer(an)
     return s, keep

@@ -219,6 +219,46 @@ def test_anisotropic_file_set(built_lib, name, tmp_path):
     np.testing.assert_array_equal(got_same, oracle.run(same))
 
 
+@pytest.mark.parametrize("variant", [0, 1, 3])
+def test_anisotropic_3d_on_the_warp_specialised_sweeps(built_lib, variant):
+    """Truly per-axis kappa / a / b maps run on the TMA warp-specialised sweeps (k_sweep_*_ws<.., ANISO = true>: 28 / 26
+    point-wise tiles per plane, 12- / 10-row tiles) by default; variant 1 forces the L1/L2-path kernels.  All equal the
+    oracle AND the reference's anisotropic sm_100 binary (tests/golden/ref_aniso3d.npz) bit for bit -- also on a grid
+    whose y / z extents are ragged against both tile heights and span several tiles and two x-chunks."""
+    from fullwave25_b200 import synthetic
+    from tests.test_oracle_golden import load_golden
+    pb = cases.make("aniso3d")
+    with engine.Engine(pb, variant=variant) as e:      # variant 3 raises if no warp-specialised plan exists
+        e.step(pb.nT)
+        e.sync()
+        np.testing.assert_array_equal(e.read_frames(0, pb.n_frames), load_golden("aniso3d"))
+    big = synthetic.make_problem((75, 67, 81), nT=36, modT=3, seed=23, aniso=True, n_air=0, n_sensors=300)
+    want_g, want = oracle.run(big, return_fields=True)
+    with engine.Engine(big, variant=variant) as e:
+        e.step(big.nT)
+        e.sync()
+        for k in "puvw":
+            np.testing.assert_array_equal(e.field(k), want[k], err_msg=k)
+        np.testing.assert_array_equal(e.read_frames(0, big.n_frames), want_g)
+    assert np.abs(want_g).max() > 0
+
+
+@pytest.mark.parametrize("fused", ["1", "0"])
+def test_anisotropic_3d_on_two_slabs(built_lib, fused, monkeypatch):
+    """The anisotropic family sharded over two x-slabs (fw25_run with a device list; both slabs on device 0 when the
+    box has one GPU): boundary sweeps of the ANISO warp-specialised kernels push their halo planes -- identical to one
+    domain and to the oracle."""
+    from fullwave25_b200 import synthetic
+    from tests.test_multi_gpu import _devices
+    monkeypatch.setenv("FW25_FUSED_HALO", fused)
+    pb = synthetic.make_problem((96, 52, 50), nT=40, modT=2, seed=24, aniso=True, n_air=0, n_sensors=200)
+    one, _ = engine.run(pb)
+    two, stats = engine.run(pb, device_ids=_devices())
+    assert stats["n_devices"] == 2 and stats["halo_bytes"] > 0 and np.abs(one).max() > 0
+    np.testing.assert_array_equal(two, one)
+    np.testing.assert_array_equal(one, oracle.run(pb))
+
+
 def test_large_host_maps_take_the_staged_upload(built_lib, monkeypatch):
     """Host maps of >= 32 MB whose rows are not a multiple of 32 floats go up densely into two staging buffers and are
     re-pitched on the device (Engine::upload_dense_rows); with 8 MB chunks every map needs five of them."""
