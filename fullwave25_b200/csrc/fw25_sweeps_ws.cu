@@ -512,8 +512,22 @@ bool tmap3d(CUtensorMap *m, const void *base, const Geom &G, int box_c, int box_
   return true;
 }
 
-constexpr int TY_WS = FW25_WS_TY;
-constexpr int MINB_WS = FW25_WS_MINB;
+// tile rows / resident CTAs per SM, per sweep (tuning: FW25_WS_TY_U=.. FW25_WS_MINB_U=.. python -m fullwave25_b200.build)
+#ifndef FW25_WS_TY_U
+#define FW25_WS_TY_U FW25_WS_TY
+#endif
+#ifndef FW25_WS_TY_P
+#define FW25_WS_TY_P FW25_WS_TY
+#endif
+#ifndef FW25_WS_MINB_U
+#define FW25_WS_MINB_U FW25_WS_MINB
+#endif
+#ifndef FW25_WS_MINB_P
+#define FW25_WS_MINB_P FW25_WS_MINB
+#endif
+constexpr int TY_U = FW25_WS_TY_U, TY_P = FW25_WS_TY_P;
+constexpr int MINB_U = FW25_WS_MINB_U, MINB_P = FW25_WS_MINB_P;
+constexpr int MINB_WS = FW25_WS_MINB;     // anisotropic family
 // Anisotropic family: 28 (fd_u) / 26 (fd_p) point-wise tiles per plane.  Tile rows chosen so that two CTAs still fit
 // one SM's 227 KB of shared memory: fd_u 12 rows (107.6 KB), fd_p 10 rows (100.1 KB).
 #ifndef FW25_WS_TY_AU
@@ -533,6 +547,8 @@ static_assert(sizeof(SmemP<TY_AP, npw_p(true)>) * 2 + 2048 <= 227 * 1024, "aniso
 //        haloed tile), and ~100 MB of point-wise tiles stream through L2 in between.  Measured at 800 x 1240 x 1240:
 //        27.66 -> 28.03 Gpt/s, DRAM bytes per updated point 113.5 -> 112.2 (fd_u), 107.1 -> 105.8 (fd_p)
 //        (profiles/ncu_r02_ws.txt): on by default.
+// (tried: cp.async.bulk.prefetch.tensor.L2 of the point-wise tiles 1-5 planes ahead: 27.6 -> 25.2 / 23.9 / 21.8 / 19.5
+//  Gpt/s, monotonically worse -- profiles/README.md; not kept)
 // bits 8..: strip width of the tile order (tile_of_block); 0 = plain z-fastest order
 int ws_hint() {
   static const int h = [] {
@@ -580,7 +596,7 @@ bool allow_smem(K kernel, size_t bytes) {
 WsPlan *ws_plan_create(const Fields &F, const Geom &G, const float *host_dmap, cudaStream_t st, std::string *err,
                        bool aniso) {
   const int n_maps = aniso ? M_END_ANISO : MP_END;
-  const int ty_u = aniso ? TY_AU : TY_WS, ty_p = aniso ? TY_AP : TY_WS;
+  const int ty_u = aniso ? TY_AU : TY_U, ty_p = aniso ? TY_AP : TY_P;
   std::vector<CUtensorMap> h(n_maps);
   bool ok = true;
   auto centre_u = [&](int slot, const void *base) { ok = ok && tmap3d(&h[slot], base, G, TZ, ty_u, err); };
@@ -631,9 +647,9 @@ WsPlan *ws_plan_create(const Fields &F, const Geom &G, const float *host_dmap, c
     attr = allow_smem(k_sweep_u_ws<TY_AU, MINB_WS, false, true>, su) && allow_smem(k_sweep_u_ws<TY_AU, MINB_WS, true, true>, su) &&
            allow_smem(k_sweep_p_ws<TY_AP, MINB_WS, false, true>, sp) && allow_smem(k_sweep_p_ws<TY_AP, MINB_WS, true, true>, sp);
   } else {
-    constexpr size_t su = sizeof(SmemU<TY_WS, NPW_U>), sp = sizeof(SmemP<TY_WS, NPW_P>);
-    attr = allow_smem(k_sweep_u_ws<TY_WS, MINB_WS, false, false>, su) && allow_smem(k_sweep_u_ws<TY_WS, MINB_WS, true, false>, su) &&
-           allow_smem(k_sweep_p_ws<TY_WS, MINB_WS, false, false>, sp) && allow_smem(k_sweep_p_ws<TY_WS, MINB_WS, true, false>, sp);
+    constexpr size_t su = sizeof(SmemU<TY_U, NPW_U>), sp = sizeof(SmemP<TY_P, NPW_P>);
+    attr = allow_smem(k_sweep_u_ws<TY_U, MINB_U, false, false>, su) && allow_smem(k_sweep_u_ws<TY_U, MINB_U, true, false>, su) &&
+           allow_smem(k_sweep_p_ws<TY_P, MINB_P, false, false>, sp) && allow_smem(k_sweep_p_ws<TY_P, MINB_P, true, false>, sp);
   }
   if (e1 != cudaSuccess || e2 != cudaSuccess ||
       cudaMemcpyAsync(pl->maps, h.data(), sizeof(CUtensorMap) * n_maps, cudaMemcpyHostToDevice, st) != cudaSuccess ||
@@ -656,28 +672,28 @@ void ws_plan_destroy(WsPlan *pl) {
 }
 
 namespace {
-template <int TY, bool ANISO>
+template <int TY, int MINB, bool ANISO>
 void launch_u(const WsPlan *pl, const Fields &F, const Geom &G, int a_lo, int a_hi, cudaStream_t st, const HaloPush *push) {
   const int Lx = pick_chunk_ws(G, a_hi - a_lo);
   constexpr size_t smem = sizeof(SmemU<TY, npw_u(ANISO)>);
   dim3 blk(TZ, TY + 1, 1);
   dim3 grd((G.nC - M + TZ - 1) / TZ, (G.nB - 2 * M + TY - 1) / TY, (a_hi - a_lo + Lx - 1) / Lx);
   if (push)
-    k_sweep_u_ws<TY, MINB_WS, true, ANISO><<<grd, blk, smem, st>>>(pl->maps, F, G, pl->tab, a_lo, a_hi, Lx, ws_hint(), *push);
+    k_sweep_u_ws<TY, MINB, true, ANISO><<<grd, blk, smem, st>>>(pl->maps, F, G, pl->tab, a_lo, a_hi, Lx, ws_hint(), *push);
   else
-    k_sweep_u_ws<TY, MINB_WS, false, ANISO><<<grd, blk, smem, st>>>(pl->maps, F, G, pl->tab, a_lo, a_hi, Lx, ws_hint(),
+    k_sweep_u_ws<TY, MINB, false, ANISO><<<grd, blk, smem, st>>>(pl->maps, F, G, pl->tab, a_lo, a_hi, Lx, ws_hint(),
                                                                     HaloPush{});
 }
-template <int TY, bool ANISO>
+template <int TY, int MINB, bool ANISO>
 void launch_p(const WsPlan *pl, const Fields &F, const Geom &G, int a_lo, int a_hi, cudaStream_t st, const HaloPush *push) {
   const int Lx = pick_chunk_ws(G, a_hi - a_lo);
   constexpr size_t smem = sizeof(SmemP<TY, npw_p(ANISO)>);
   dim3 blk(TZ, TY + 1, 1);
   dim3 grd((G.nC - M + TZ - 1) / TZ, (G.nB - 2 * M + TY - 1) / TY, (a_hi - a_lo + Lx - 1) / Lx);
   if (push)
-    k_sweep_p_ws<TY, MINB_WS, true, ANISO><<<grd, blk, smem, st>>>(pl->maps, F, G, pl->tab, a_lo, a_hi, Lx, ws_hint(), *push);
+    k_sweep_p_ws<TY, MINB, true, ANISO><<<grd, blk, smem, st>>>(pl->maps, F, G, pl->tab, a_lo, a_hi, Lx, ws_hint(), *push);
   else
-    k_sweep_p_ws<TY, MINB_WS, false, ANISO><<<grd, blk, smem, st>>>(pl->maps, F, G, pl->tab, a_lo, a_hi, Lx, ws_hint(),
+    k_sweep_p_ws<TY, MINB, false, ANISO><<<grd, blk, smem, st>>>(pl->maps, F, G, pl->tab, a_lo, a_hi, Lx, ws_hint(),
                                                                     HaloPush{});
 }
 }  // namespace
@@ -685,16 +701,16 @@ void launch_p(const WsPlan *pl, const Fields &F, const Geom &G, int a_lo, int a_
 int launch_sweep_u_ws(const WsPlan *pl, const Fields &F, const Geom &G, int a_lo, int a_hi, cudaStream_t st,
                       const HaloPush *push) {
   if (a_hi <= a_lo) return 0;
-  if (pl->aniso) launch_u<TY_AU, true>(pl, F, G, a_lo, a_hi, st, push);
-  else launch_u<TY_WS, false>(pl, F, G, a_lo, a_hi, st, push);
+  if (pl->aniso) launch_u<TY_AU, MINB_WS, true>(pl, F, G, a_lo, a_hi, st, push);
+  else launch_u<TY_U, MINB_U, false>(pl, F, G, a_lo, a_hi, st, push);
   return 1;
 }
 
 int launch_sweep_p_ws(const WsPlan *pl, const Fields &F, const Geom &G, int a_lo, int a_hi, cudaStream_t st,
                       const HaloPush *push) {
   if (a_hi <= a_lo) return 0;
-  if (pl->aniso) launch_p<TY_AP, true>(pl, F, G, a_lo, a_hi, st, push);
-  else launch_p<TY_WS, false>(pl, F, G, a_lo, a_hi, st, push);
+  if (pl->aniso) launch_p<TY_AP, MINB_WS, true>(pl, F, G, a_lo, a_hi, st, push);
+  else launch_p<TY_P, MINB_P, false>(pl, F, G, a_lo, a_hi, st, push);
   return 1;
 }
 

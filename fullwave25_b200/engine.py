@@ -8,6 +8,7 @@ raises.  (The reference behaves the same way: without its GPU binary `Launcher.r
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 import numpy as np
@@ -16,6 +17,8 @@ from .problem import MAP_NAMES, Problem
 
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libfw25.so"
+if os.environ.get("FW25_LIB"):          # tuning sweeps only (tools/build_variants.py): another build of the same library
+    LIB_PATH = Path(os.environ["FW25_LIB"]).resolve()
 _F = C.POINTER(C.c_float)
 _I = C.POINTER(C.c_int32)
 
