@@ -14,8 +14,9 @@ out.mkdir(parents=True, exist_ok=True)
 objs = [str(o) for o in sorted((B.PKG / "build").glob("*.o")) if o.name not in ("fw25_cli.o", "fw25_sweeps_ws.o")]
 for spec in sys.argv[1:]:
     name, vals = spec.split(":")
-    tyu, mu, typ, mp = vals.split(",")
+    tyu, mu, typ, mp, *extra = vals.split(",")
     defs = [f"-DFW25_WS_TY_U={tyu}", f"-DFW25_WS_MINB_U={mu}", f"-DFW25_WS_TY_P={typ}", f"-DFW25_WS_MINB_P={mp}"]
+    defs += [f"-D{e}" for e in extra]          # e.g. FW25_EXPERIMENT_FAST_DIV (timing experiment, not bit-exact)
     obj = out / f"ws_{name}.o"
     r = subprocess.run([nvcc, *B.NVCC_FLAGS, *defs, *B._host_cxx(), "-c", "-o", str(obj), str(B.CSRC / "fw25_sweeps_ws.cu")],
                        capture_output=True, text=True)
