@@ -373,17 +373,36 @@ def run_ours(args):
         free_device()
 
     # ---- (5) end to end through the public API from HOST buffers
+    def free_host():
+        """Give pinned host memory back to the OS (torch caches it): the two end-to-end variants pin up to 70 GB per
+        rank one after the other."""
+        import gc
+        gc.collect()
+        try:
+            torch._C._host_emptyCache()
+        except Exception:  # noqa: BLE001
+            pass
+
     e2e = None
     if not args.no_e2e:
-        holder = [maps_full]                                # hand the device maps over: run_e2e must be able to free them
-        maps_full = None
-        hostmaps = run_e2e(args, rank, world, dev, comm, (main, bnd), pb_full, holder, frames_resident, barrier, max_over_ranks)
         if world == 1:
+            holder = [maps_full]                            # hand the device maps over: run_e2e must be able to free them
+            maps_full = None
+            hostmaps = run_e2e(args, rank, world, dev, comm, (main, bnd), pb_full, holder, frames_resident, barrier,
+                               max_over_ranks)
             free_device()
+            free_host()
             e2e = run_e2e_medium(args, dev)
             e2e["hostmaps_variant"] = hostmaps
         else:
-            e2e = hostmaps
+            maps_full = None
+            free_device()
+            e2e = run_e2e_medium_slabs(args, rank, world, dev, comm, (main, bnd), barrier, max_over_ranks)
+            free_device()
+            free_host()
+            e2e["hostmaps_variant"] = run_e2e(args, rank, world, dev, comm, (main, bnd), pb_full, [None],
+                                              frames_resident, barrier, max_over_ranks)
+        free_host()
 
     if rank == 0:
         config["same_grid"] = same
@@ -497,6 +516,91 @@ def run_e2e_medium(args, dev, max_mismatch_report: int = 4):
     return e2e
 
 
+def run_e2e_medium_slabs(args, rank, world, dev, comm, streams, barrier, max_over_ranks):
+    """N > 1: the same job from the USER-grid medium, one process per GPU.  Every rank holds, in pinned host memory, the
+    user-grid planes its x-slab reads (sound_speed, density, beta, alpha_coeff, alpha_power, float32); inside the timed
+    region it uploads them, builds its own slab of the 14 engine maps on its GPU (`fw25_mapgen_slab`: ghost planes
+    included, no 14-map upload), creates the engine on those maps in place, runs the K steps with NCCL halos and the
+    sensor frames are gathered on rank 0."""
+    import torch
+    import torch.distributed as dist
+    from fullwave25_b200 import lut_standin, mapgen, synthetic_device
+    from fullwave25_b200.problem import MAP_NAMES, Problem
+    from fullwave25_b200.runtime import SlabEngine, gather_frames
+    from fullwave25_b200.slab import SlabDriver, partition
+    main, bnd = streams
+    nXl, nY, nZ = args.grid
+    K = args.steps
+    gX = nXl * world
+    nb = 8 + MEDIUM["n_pml"] + MEDIUM["n_trans"]
+    user = (gX - 2 * nb, nY - 2 * nb, nZ - 2 * nb)
+    slab = partition(gX, world)[rank]
+    u0 = min(max(slab.gx0 - nb, 0), user[0] - 1)
+    u1 = min(max(slab.gx1 - 1 - nb, 0), user[0] - 1) + 1
+    f0, c0, ppw, cfl = 1e6, 1540.0, 12, 0.2
+    dx = c0 / f0 / ppw
+    dt = cfl * dx / c0
+    import psutil
+    need = 5 * (u1 - u0) * user[1] * user[2] * 4
+    ok = torch.tensor([1.0 if need * 1.5 < psutil.virtual_memory().available / world else 0.0], device=dev)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if ok.item() == 0.0:
+        return {"unavailable": f"host RAM: {need / 1e9:.0f} GB of pinned user-grid planes per rank"}
+    um, c_min, c_max, pinned = synthetic_device.make_user_medium(user, device=dev, block=MEDIUM["block"],
+                                                                 seed=MEDIUM["seed"], x_range=(u0, u1))
+    lim = torch.tensor([-c_min, c_max], device=dev, dtype=torch.float64)     # the stencil table spans the WHOLE medium
+    dist.all_reduce(lim, op=dist.ReduceOp.MAX)
+    c_min, c_max = -float(lim[0].item()), float(lim[1].item())
+    spec = mapgen.MediumSpec(user_shape=user, dt=dt, dx=dx, c0=c0, cfl=cfl, sound_speed=um["sound_speed"],
+                             density=um["density"], beta=um["beta"], alpha_coeff=um["alpha_coeff"],
+                             alpha_power=um["alpha_power"], lut=lut_standin.lookup_table(),
+                             n_pml_layer=MEDIUM["n_pml"], n_transition_layer=MEDIUM["n_trans"], dcmap_full3d=True,
+                             extra={"c_min": c_min, "c_max": c_max}, user_planes=(u0, u1 - u0))
+    _, dmap, ndmap, _ = spec.stencil_tables()
+    nTic = min(K, int(np.ceil(2.0 / f0 / dt)) + 1)
+    icc, icmat, outc, icczero = synthetic_device._lists(gX, nY, nZ, nb, nTic, dt, dx, f0=f0, c0=c0, seed=MEDIUM["seed"],
+                                                        n_sensors=MEDIUM["n_sensors"], n_air=MEDIUM["n_air"],
+                                                        source_layers=3, amp=1e5)
+    icm = torch.empty(icmat.shape, dtype=torch.float32, pin_memory=True)
+    icm.numpy()[...] = icmat
+    none = {name: None for name in MAP_NAMES}
+    pb = Problem(ndim=3, nX=slab.n_local, nY=nY, nZ=nZ, nT=K, nTic=nTic, modT=MEDIUM["modT"], ndmap=ndmap,
+                 dX=float(np.float32(dx)), dT=float(np.float32(dt)), **none, dmap=dmap, dcmap=None, icc=icc,
+                 icmat=icm.numpy(), outc=outc, icczero=icczero, extra={}, dcmap_full3d=True)
+    h2d = sum(t.numel() * 4 for t in pinned.values()) + icm.numel() * 4 + icc.nbytes
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    barrier()
+    t0 = time.perf_counter()
+    ms = mapgen.MapSet(spec, device=dev.index or 0, planes=(slab.gx0, slab.gx1))
+    eng = SlabEngine(pb, slab, dev, device_maps=ms.device_maps())
+    eng.eng.sync()
+    t_setup = time.perf_counter() - t0
+    drv = SlabDriver(slab, eng, comm, pb.modT, streams=(main, bnd), ndim=3)
+    for _ in range(K):
+        drv.step()
+    out = gather_frames(drv, eng, pb.n_frames, pb.ncoordsout, dist)
+    barrier()
+    dt_e2e = max_over_ranks(time.perf_counter() - t0)
+    e2e = {"value": gX * nY * nZ * K / dt_e2e / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d / K,
+           "d2h_bytes_per_step": pb.n_frames * eng.eng.n_local_sensors * 4 / K, "seconds": dt_e2e,
+           "setup_seconds": t_setup, "mapgen_upload_ms": ms.upload_ms, "mapgen_kernel_ms": ms.kernel_ms,
+           "api": "per rank: fw25_mapgen_slab (C-ABI; this rank's user-grid planes in pinned host memory -> its slab of "
+                  "the engine maps in HBM) + fw25_create on those maps + SlabDriver.step (NCCL halos) + gather_frames",
+           "grid_per_gpu": f"{nXl}x{nY}x{nZ}", "user_grid": "x".join(map(str, user)),
+           "user_planes_rank0": [int(u0), int(u1)], "input_dtype": "float32", "launches": int(eng.eng.launches),
+           "finite": bool(np.isfinite(out).all()) if out is not None else None,
+           "absmax": float(np.abs(out).max()) if out is not None and out.size else None,
+           "nonzero_frame_values": int((out != 0).sum()) if out is not None else None,
+           "relaxation_table": "stand-in (fullwave25_b200/lut_standin.py)",
+           "parity": "slab maps == whole-grid maps byte for byte (tests/test_mapgen_gpu.py); N ranks == 1 rank "
+                     "(parity_n_vs_1, tests/test_multi_gpu.py)"}
+    eng.close()
+    ms.close()
+    del pinned
+    return e2e
+
+
 def run_e2e(args, rank, world, dev, comm, streams, pb, maps_holder, frames_chk, barrier, max_over_ranks):
     """The same job through the public API with HOST buffers: pinned host maps -> upload -> K steps -> frames."""
     maps = maps_holder.pop()
@@ -518,7 +622,12 @@ def run_e2e(args, rank, world, dev, comm, streams, pb, maps_holder, frames_chk, 
         pb, maps = synthetic_device.make_slab(gshape, slab.gx0, slab.gx1, device=dev, nT=K, **MEDIUM)
     need = 14 * slab.n_local * nY * nZ * 4
     avail = psutil.virtual_memory().available / max(world, 1)
-    if need * 1.25 > avail:
+    fits = need * 1.25 <= avail
+    if world > 1:                                       # one decision for all ranks (the ranks meet at barriers below)
+        ok = torch.tensor([1.0 if fits else 0.0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        fits = ok.item() != 0.0
+    if not fits:
         return {"unavailable": f"host RAM: {need / 1e9:.0f} GB of pinned maps per rank, {avail / 1e9:.0f} GB available"}
     pb = dataclasses.replace(pb, nT=K, nTic=min(pb.nTic, K))
     pb.icmat = np.ascontiguousarray(pb.icmat[:, : pb.nTic])

@@ -343,11 +343,11 @@ void Engine::init(const fw25_problem &pb, const fw25_slab *slab, int dev) {
     if (!ws) fail(2, "warp-specialised anisotropic sweep setup failed: " + perr);
   }
 
-  if (!aniso && sweeps2d_supported(ndim, G)) {
+  if (sweeps2d_supported(ndim, G)) {
     std::string perr;
     std::vector<float> hd((size_t)18 * pb.ndmap);
     memcpy(hd.data(), pb.dmap, hd.size() * 4);
-    p2d = plan2d_create(F, G, hd.data(), stream, &perr);
+    p2d = plan2d_create(F, G, hd.data(), stream, &perr, aniso);
     if (!p2d) fail(2, "2D sweep setup failed: " + perr);
   }
 
@@ -448,7 +448,7 @@ void Engine::build_fuse_lists() {
   fuse_ok = false;
   const char *ev = getenv("FW25_FUSE2D");
   if (!ev || atoi(ev) == 0) return;
-  if (ndim != 2 || !p2d || own_lo != 0 || own_hi != nX_global || n_src_rim > 0 || !sweeps2d_fusable()) return;
+  if (ndim != 2 || !p2d || aniso || own_lo != 0 || own_hi != nX_global || n_src_rim > 0 || !sweeps2d_fusable()) return;
   const int a_lo = G.a_rim_lo, a_hi = G.a_rim_hi;
   if (a_hi <= a_lo) return;
   const int n_bx = (G.nC - M + 127) / 128, n_by = (a_hi - a_lo + FUSE_TR - 1) / FUSE_TR;

@@ -53,7 +53,8 @@ int launch_sweep_p_ws(const WsPlan *pl, const Fields &F, const Geom &G, int a_lo
 struct Plan2D;
 bool sweeps2d_supported(int ndim, const Geom &G);
 bool sweeps2d_worthwhile(const Geom &G, int rows);   // auto mode: tiled only where it beats the simple sweeps
-Plan2D *plan2d_create(const Fields &F, const Geom &G, const float *host_dmap, cudaStream_t st, std::string *err);
+Plan2D *plan2d_create(const Fields &F, const Geom &G, const float *host_dmap, cudaStream_t st, std::string *err,
+                      bool aniso = false);   // aniso: per-axis kappa / a / b maps (Fields::kv .. bp)
 void plan2d_destroy(Plan2D *pl);
 int launch_sweep_u_2d(const Plan2D *pl, const Fields &F, const Geom &G, int a_lo, int a_hi, cudaStream_t st);
 int launch_sweep_p_2d(const Plan2D *pl, const Fields &F, const Geom &G, int a_lo, int a_hi, cudaStream_t st);

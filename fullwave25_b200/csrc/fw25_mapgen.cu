@@ -83,6 +83,7 @@ struct MgParams {
   const void *alpha_coeff, *alpha_power;
   int in_f32, u_plane0;
   int a0;                  // first extended plane of this launch (blockIdx.z = 0)
+  int a_base;              // extended plane stored at index 0 of the outputs (0, or an x-slab's first plane)
   const double *lut, *lut_alpha, *lut_power;
   const unsigned char *lut_invalid;
   int lut_na, lut_np;
@@ -131,7 +132,7 @@ __global__ void __launch_bounds__(256) k_mapgen(const MgParams P) {
   const int b = blockIdx.y;
   const int a = blockIdx.z + P.a0;
   if (c >= P.pitch) return;
-  const long long o = ((long long)a * P.nB + b) * P.pitch + c;
+  const long long o = ((long long)(a - P.a_base) * P.nB + b) * P.pitch + c;
   if (c >= P.nC) {   // padding: zeros, like the engine's own uploads
 #pragma unroll
     for (int i = 0; i < 13; ++i) P.out[i][o] = 0.0f;
@@ -218,7 +219,8 @@ using namespace fw25;
 
 struct fw25_mapset {
   int device = 0;
-  int ndim = 3, nX = 0, nY = 0, nZ = 1, pitch = 0;
+  int ndim = 3, nX = 0, nY = 0, nZ = 1, pitch = 0;   // nX: planes held (an x-slab: fewer than the extended grid's)
+  int x0 = 0;                                          // extended plane of the first plane held
   int dcmap_full3d = 1;
   size_t cells = 0;
   float *block = nullptr;    // one allocation: the 13 maps, then dcmap
@@ -253,7 +255,8 @@ struct MapgenPlan {
     if (tables) cudaFree(tables);
   }
 
-  void create(const fw25_medium *md, int device, cudaStream_t st) {
+  // a_first / a_count: the extended x planes to hold ([0, nA) by default; an x-slab otherwise)
+  void create(const fw25_medium *md, int device, cudaStream_t st, int a_first = 0, int a_count = -1) {
     if (md->ndim != 2 && md->ndim != 3) mg_fail("fw25_mapgen: ndim must be 2 or 3");
     const int ndim = md->ndim;
     const int nz_u = ndim == 3 ? md->nz : 1;
@@ -281,13 +284,16 @@ struct MapgenPlan {
     MG_CUDA(cudaSetDevice(device));
     ms.reset(new fw25_mapset());
     ms->device = device;
-    ms->ndim = ndim; ms->nX = (int)ex; ms->nY = (int)ey; ms->nZ = (int)ez;
+    if (a_count < 0) a_count = (int)ex - a_first;
+    if (a_first < 0 || a_count <= 0 || a_first + (long long)a_count > ex) mg_fail("fw25_mapgen: plane range outside the extended grid");
+    ms->ndim = ndim; ms->nX = a_count; ms->x0 = a_first; ms->nY = (int)ey; ms->nZ = (int)ez;
     ms->dcmap_full3d = md->dcmap_full3d != 0 || ndim == 2;
 
     P.ndim = ndim;
     P.nA = (int)ex; P.nB = ndim == 3 ? (int)ey : 1; P.nC = ndim == 3 ? (int)ez : (int)ey;
     P.uA = md->nx; P.uB = ndim == 3 ? md->ny : 1; P.uC = ndim == 3 ? nz_u : md->ny;
     P.pitch = fw25_pitch(P.nC);
+    P.a_base = a_first;
     ms->pitch = P.pitch;
     P.nb = nb; P.use_pml = md->use_pml != 0;
     P.dt = md->dt; P.d_target = md->d_target_pml;
@@ -352,7 +358,7 @@ struct MapgenPlan {
     }
     MG_CUDA(cudaStreamSynchronize(st));             // the host vectors above go out of scope
 
-    ms->cells = (size_t)P.nA * P.nB * P.pitch;
+    ms->cells = (size_t)a_count * P.nB * P.pitch;
     MG_CUDA(cudaMalloc((void **)&ms->block, ms->cells * 4 * 14));
     for (int i = 0; i < 13; ++i) P.out[i] = ms->maps[i] = ms->block + (size_t)i * ms->cells;
     P.dcmap = ms->dcmap = reinterpret_cast<int32_t *>(ms->block + (size_t)13 * ms->cells);
@@ -538,7 +544,9 @@ void mapstream_destroy(MapStream *S) { delete S; }
 
 extern "C" {
 
-int fw25_mapgen(const fw25_medium *md, int32_t device, fw25_mapset **out, double *stats_ms) {
+// extended planes [gx0, gx1) from host arrays that hold the user-grid planes [u_plane0, u_plane0 + u_planes)
+static int mapgen_impl(const fw25_medium *md, int32_t device, int gx0, int gx1, int u_plane0, int u_planes,
+                       fw25_mapset **out, double *stats_ms) {
   if (!md || !out) { g_err = "fw25_mapgen: NULL argument"; return 1; }
   *out = nullptr;
   MapgenPlan plan;
@@ -550,20 +558,27 @@ int fw25_mapgen(const fw25_medium *md, int32_t device, fw25_mapset **out, double
     MG_CUDA(cudaSetDevice(device));
     MG_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     for (auto &e : ev) MG_CUDA(cudaEventCreate(&e));
-    plan.create(md, device, st);
+    plan.create(md, device, st, gx0, gx1 < 0 ? -1 : gx1 - gx0);
+    const int a_lo = plan.ms->x0, a_hi = plan.ms->x0 + plan.ms->nX;
+    int first, last;
+    plan.user_range(a_lo, a_hi, first, last);
+    if (u_planes < 0) { u_plane0 = 0; u_planes = plan.P.uA; }
+    if (first < u_plane0 || last >= u_plane0 + u_planes)
+      mg_fail("fw25_mapgen_slab: the host arrays do not hold the user-grid planes this slab reads");
     // One scratch allocation for the user-grid inputs and one output allocation: a handful of driver calls whatever
     // the number of maps.
-    const size_t per = ((size_t)plan.P.uA * plan.user_plane * plan.elem + 255) / 256 * 256;
+    const size_t plane_bytes = plan.user_plane * plan.elem, need = (size_t)(last - first + 1) * plane_bytes;
+    const size_t per = (need + 255) / 256 * 256;
     MG_CUDA(cudaMalloc(&scratch, per * plan.n_user));
     MG_CUDA(cudaEventRecord(ev[0], st));
     void *dev_user[13];
     for (int i = 0; i < plan.n_user; ++i) {
       dev_user[i] = static_cast<char *>(scratch) + (size_t)i * per;
-      MG_CUDA(cudaMemcpyAsync(dev_user[i], plan.host_user[i], (size_t)plan.P.uA * plan.user_plane * plan.elem,
-                              cudaMemcpyHostToDevice, st));
+      MG_CUDA(cudaMemcpyAsync(dev_user[i], static_cast<const char *>(plan.host_user[i]) + (size_t)(first - u_plane0) * plane_bytes,
+                              need, cudaMemcpyHostToDevice, st));
     }
     MG_CUDA(cudaEventRecord(ev[1], st));
-    plan.launch(0, plan.P.nA, dev_user, 0, st);
+    plan.launch(a_lo, a_hi, dev_user, first, st);
     MG_CUDA(cudaEventRecord(ev[2], st));
     plan.ms->invalid = plan.read_invalid(st);
     if (stats_ms) {
@@ -582,6 +597,16 @@ int fw25_mapgen(const fw25_medium *md, int32_t device, fw25_mapset **out, double
   if (rc) return rc;
   *out = plan.ms.release();
   return 0;
+}
+
+int fw25_mapgen(const fw25_medium *md, int32_t device, fw25_mapset **out, double *stats_ms) {
+  return mapgen_impl(md, device, 0, -1, 0, -1, out, stats_ms);
+}
+
+int fw25_mapgen_slab(const fw25_medium *md, int32_t device, int32_t gx0, int32_t gx1, int32_t u_plane0, int32_t u_planes,
+                     fw25_mapset **out, double *stats_ms) {
+  if (gx1 <= gx0 || u_planes <= 0) { g_err = "fw25_mapgen_slab: empty plane range"; return 1; }
+  return mapgen_impl(md, device, gx0, gx1, u_plane0, u_planes, out, stats_ms);
 }
 
 int fw25_mapset_problem(const fw25_mapset *ms, fw25_problem *pb) {

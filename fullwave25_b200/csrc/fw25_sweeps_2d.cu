@@ -47,12 +47,21 @@ struct PwU {   // point-wise operands of one cell of fd_u
   float rho, K, kx, a1, b1, a2, b2, mA1, mA2, mC1, mC2, qA, qC;
   int ci;
 };
+struct PwAx {  // anisotropic family: kappa / a / b of the contiguous axis (the reference's y); axis x sits in Pw*
+  float k, a1, b1, a2, b2;
+};
 
 // read-only maps (never written during a run: safe before pdl_wait) ...
 __device__ __forceinline__ void load_maps_u(PwU &w, const Fields &F, long long i) {
   w.ci = __ldg(F.dcmap + i);
   w.rho = __ldg(F.rho + i); w.K = __ldg(F.K + i); w.kx = __ldg(F.kappax + i);
   w.a1 = __ldg(F.ax1 + i); w.b1 = __ldg(F.bx1 + i); w.a2 = __ldg(F.ax2 + i); w.b2 = __ldg(F.bx2 + i);
+}
+__device__ __forceinline__ PwAx load_axis_c_u(const Fields &F, long long i) {
+  return PwAx{__ldg(F.kv[2] + i), __ldg(F.av[2][0] + i), __ldg(F.bv[2][0] + i), __ldg(F.av[2][1] + i), __ldg(F.bv[2][1] + i)};
+}
+__device__ __forceinline__ PwAx load_axis_c_p(const Fields &F, long long i) {
+  return PwAx{__ldg(F.kp[2] + i), __ldg(F.ap[2][0] + i), __ldg(F.bp[2][0] + i), __ldg(F.ap[2][1] + i), __ldg(F.bp[2][1] + i)};
 }
 // ... and the state the previous sweeps wrote
 __device__ __forceinline__ void load_state_u(PwU &w, const Fields &F, long long i) {
@@ -253,7 +262,7 @@ __global__ void __launch_bounds__(TC2, FW25_WS_2D_MINB)
 // shortest possible dependency chain (no marching).  The tile-height sweep on a B200 (profiles/sweep_2d_r01.txt)
 // showed the single-row marching tiles beating the taller marching ones at every 2D size -- parallelism matters
 // more than halo traffic there -- so this form keeps one cell per thread and shares the tile instead.
-template <int TR>
+template <int TR, bool ANISO>
 __global__ void __launch_bounds__(TC2 * TR)
     k_sweep_u_2dc(const __grid_constant__ CUtensorMap map_p, const Fields F, const Geom G,
                   const StencilTab2 *__restrict__ tab, int a_lo, int a_hi) {
@@ -273,9 +282,11 @@ __global__ void __launch_bounds__(TC2 * TR)
   const bool act = c >= M && c < G.nC - M && a < a_hi;
   const long long i = (long long)a * G.sA + c;
   PwU w{};
+  PwAx wc{};
   StencilTab2 T{};
   if (act) {                                     // coefficient maps and the stencil table: in flight before ...
     load_maps_u(w, F, i);
+    if constexpr (ANISO) wc = load_axis_c_u(F, i);
     T = tab[w.ci];
   }
   pdl_wait();                                    // ... the previous kernel (injection / fd_p: they write p) is done
@@ -304,12 +315,13 @@ __global__ void __launch_bounds__(TC2 * TR)
   gA = div_(fma_(E, cA, gA), dX);
   gC = div_(fma_(E, cC, gC), dX);
   const float s = div_(div_(G.dT, w.rho), fma_(rcp_(w.K), pcen, 1.0f));
+  if constexpr (!ANISO) wc = PwAx{w.kx, w.a1, w.b1, w.a2, w.b2};
   const float mA1 = fma_(w.b1, w.mA1, mul_(gA, w.a1));
   const float mA2 = fma_(w.b2, w.mA2, mul_(gA, w.a2));
-  const float mC1 = fma_(w.b1, w.mC1, mul_(gC, w.a1));
-  const float mC2 = fma_(w.b2, w.mC2, mul_(gC, w.a2));
+  const float mC1 = fma_(wc.b1, w.mC1, mul_(gC, wc.a1));
+  const float mC2 = fma_(wc.b2, w.mC2, mul_(gC, wc.a2));
   const float qA = fma_(-s, add_(add_(div_(gA, w.kx), mA1), mA2), w.qA);
-  const float qC = fma_(-s, add_(add_(div_(gC, w.kx), mC1), mC2), w.qC);
+  const float qC = fma_(-s, add_(add_(div_(gC, wc.k), mC1), mC2), w.qC);
   __stcs(F.psi[0][0] + i, mA1); __stcs(F.psi[0][1] + i, mA2);
   __stcs(F.psi[2][0] + i, mC1); __stcs(F.psi[2][1] + i, mC2);
   F.q[0][i] = qA; F.q[2][i] = qC;
@@ -321,7 +333,7 @@ __global__ void __launch_bounds__(TC2 * TR)
 // of four).  Sensors: box sensors by arithmetic on the cell's own coordinates; listed sensors, sources and air voxels
 // through a per-tile CSR list built at setup (most tiles have none: two int loads per CTA).  A cell that is both
 // sensor and source is recorded from the register / shared copy of p' before the injected value lands.
-template <int TR, bool FUSED>
+template <int TR, bool FUSED, bool ANISO>
 __global__ void __launch_bounds__(TC2 * TR)
     k_sweep_p_2dc(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_v, const Fields F,
                   const Geom G, const StencilTab2 *__restrict__ tab, int a_lo, int a_hi, const Fuse2D X, int t_off,
@@ -344,10 +356,12 @@ __global__ void __launch_bounds__(TC2 * TR)
   const bool act = c >= M && c < G.nC - M && a < a_hi;
   const long long i = (long long)a * G.sA + c;
   PwP w{};
+  PwAx wc{};
   StencilTab2 T{};
   int e0 = 0, e1 = 0;
   if (act) {
     load_maps_p(w, F, i);
+    if constexpr (ANISO) wc = load_axis_c_p(F, i);
     T = tab[w.ci];
   }
   if (FUSED) {                                   // the tile's list bounds are setup data too
@@ -381,11 +395,12 @@ __global__ void __launch_bounds__(TC2 * TR)
     const float dX = G.dX;
     hA = div_(fma_(E, cA, hA), dX);
     hC = div_(fma_(E, cC, hC), dX);
+    if constexpr (!ANISO) wc = PwAx{w.ku, w.a1, w.b1, w.a2, w.b2};
     const float fA1 = fma_(w.b1, w.fA1, mul_(hA, w.a1));
     const float fA2 = fma_(w.b2, w.fA2, mul_(hA, w.a2));
-    const float fC1 = fma_(w.b1, w.fC1, mul_(hC, w.a1));
-    const float fC2 = fma_(w.b2, w.fC2, mul_(hC, w.a2));
-    float S = add_(div_(hA, w.ku), div_(hC, w.ku));
+    const float fC1 = fma_(wc.b1, w.fC1, mul_(hC, wc.a1));
+    const float fC2 = fma_(wc.b2, w.fC2, mul_(hC, wc.a2));
+    float S = add_(div_(hA, w.ku), div_(hC, wc.k));
     S = add_(fA1, S); S = add_(fA2, S); S = add_(fC1, S); S = add_(fC2, S);
     const float At = mul_(mul_(G.dT, w.K), S);
     const float Bt = fma_(w.p, mul_(rcp_(w.K), sub_(1.0f, add_(w.beta, w.beta))), 1.0f);
@@ -463,6 +478,7 @@ constexpr int kRpt[4] = {1, 2, 4, 8};    // rows per CTA the kernels are instant
 static int rpt_slot(int rpt) { return rpt == 1 ? 0 : rpt == 2 ? 1 : rpt == 4 ? 2 : 3; }
 
 struct Plan2D {
+  bool aniso = false;            // per-axis kappa / a / b maps: the ANISO one-cell-per-thread tiles (TR = 2) only
   StencilTab2 *tab = nullptr;
   CUtensorMap p[4], u[4], v[4];   // one set of boxes per entry of kRpt
 };
@@ -479,8 +495,10 @@ bool sweeps2d_worthwhile(const Geom &G, int rows) {
   return (long long)rows * G.nC >= thr;
 }
 
-Plan2D *plan2d_create(const Fields &F, const Geom &G, const float *host_dmap, cudaStream_t st, std::string *err) {
+Plan2D *plan2d_create(const Fields &F, const Geom &G, const float *host_dmap, cudaStream_t st, std::string *err,
+                      bool aniso) {
   auto *pl = new Plan2D();
+  pl->aniso = aniso;
   bool ok = true;
   for (int v = 0; v < 4 && ok; ++v) {
     const int rpt = kRpt[v];
@@ -533,12 +551,14 @@ static int pick_tr() {
 
 int launch_sweep_u_2d(const Plan2D *pl, const Fields &F, const Geom &G, int a_lo, int a_hi, cudaStream_t st) {
   if (a_hi <= a_lo) return 0;
-  if (const int tr = pick_tr()) {
+  if (const int tr = pl->aniso ? 2 : pick_tr()) {
     dim3 grd((G.nC - M + TC2 - 1) / TC2, (a_hi - a_lo + tr - 1) / tr, 1), blk(TC2, tr, 1);
     const CUtensorMap &mp = pl->p[rpt_slot(tr)];
-    if (tr == 8) launch_pdl(k_sweep_u_2dc<8>, grd, blk, 0, st, mp, F, G, pl->tab, a_lo, a_hi);
-    else if (tr == 4) launch_pdl(k_sweep_u_2dc<4>, grd, blk, 0, st, mp, F, G, pl->tab, a_lo, a_hi);
-    else launch_pdl(k_sweep_u_2dc<2>, grd, blk, 0, st, mp, F, G, pl->tab, a_lo, a_hi);
+    if (pl->aniso) launch_pdl(k_sweep_u_2dc<2, true>, dim3(grd.x, (a_hi - a_lo + 1) / 2, 1), dim3(TC2, 2, 1), 0, st,
+                              pl->p[rpt_slot(2)], F, G, pl->tab, a_lo, a_hi);
+    else if (tr == 8) launch_pdl(k_sweep_u_2dc<8, false>, grd, blk, 0, st, mp, F, G, pl->tab, a_lo, a_hi);
+    else if (tr == 4) launch_pdl(k_sweep_u_2dc<4, false>, grd, blk, 0, st, mp, F, G, pl->tab, a_lo, a_hi);
+    else launch_pdl(k_sweep_u_2dc<2, false>, grd, blk, 0, st, mp, F, G, pl->tab, a_lo, a_hi);
     return 1;
   }
   const int rpt = pick_rpt(G, a_hi - a_lo);
@@ -553,13 +573,15 @@ int launch_sweep_u_2d(const Plan2D *pl, const Fields &F, const Geom &G, int a_lo
 
 int launch_sweep_p_2d(const Plan2D *pl, const Fields &F, const Geom &G, int a_lo, int a_hi, cudaStream_t st) {
   if (a_hi <= a_lo) return 0;
-  if (const int tr = pick_tr()) {
+  if (const int tr = pl->aniso ? 2 : pick_tr()) {
     dim3 grd((G.nC - M + TC2 - 1) / TC2, (a_hi - a_lo + tr - 1) / tr, 1), blk(TC2, tr, 1);
     const CUtensorMap &mu = pl->u[rpt_slot(tr)], &mv = pl->v[rpt_slot(tr)];
     const Fuse2D none{};
-    if (tr == 8) launch_pdl(k_sweep_p_2dc<8, false>, grd, blk, 0, st, mu, mv, F, G, pl->tab, a_lo, a_hi, none, 0, 0);
-    else if (tr == 4) launch_pdl(k_sweep_p_2dc<4, false>, grd, blk, 0, st, mu, mv, F, G, pl->tab, a_lo, a_hi, none, 0, 0);
-    else launch_pdl(k_sweep_p_2dc<2, false>, grd, blk, 0, st, mu, mv, F, G, pl->tab, a_lo, a_hi, none, 0, 0);
+    if (pl->aniso) launch_pdl(k_sweep_p_2dc<2, false, true>, dim3(grd.x, (a_hi - a_lo + 1) / 2, 1), dim3(TC2, 2, 1), 0, st,
+                              pl->u[rpt_slot(2)], pl->v[rpt_slot(2)], F, G, pl->tab, a_lo, a_hi, none, 0, 0);
+    else if (tr == 8) launch_pdl(k_sweep_p_2dc<8, false, false>, grd, blk, 0, st, mu, mv, F, G, pl->tab, a_lo, a_hi, none, 0, 0);
+    else if (tr == 4) launch_pdl(k_sweep_p_2dc<4, false, false>, grd, blk, 0, st, mu, mv, F, G, pl->tab, a_lo, a_hi, none, 0, 0);
+    else launch_pdl(k_sweep_p_2dc<2, false, false>, grd, blk, 0, st, mu, mv, F, G, pl->tab, a_lo, a_hi, none, 0, 0);
     return 1;
   }
   const int rpt = pick_rpt(G, a_hi - a_lo);
@@ -580,7 +602,7 @@ int launch_sweep_p_2d_fused(const Plan2D *pl, const Fields &F, const Geom &G, in
   if (a_hi <= a_lo) return 0;
   dim3 grd((G.nC - M + TC2 - 1) / TC2, (a_hi - a_lo + FUSE_TR - 1) / FUSE_TR, 1), blk(TC2, FUSE_TR, 1);
   const CUtensorMap &mu = pl->u[rpt_slot(FUSE_TR)], &mv = pl->v[rpt_slot(FUSE_TR)];
-  launch_pdl(k_sweep_p_2dc<FUSE_TR, true>, grd, blk, 0, st, mu, mv, F, G, pl->tab, a_lo, a_hi, X, t_off, flags);
+  launch_pdl(k_sweep_p_2dc<FUSE_TR, true, false>, grd, blk, 0, st, mu, mv, F, G, pl->tab, a_lo, a_hi, X, t_off, flags);
   return 1;
 }
 

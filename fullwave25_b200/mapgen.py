@@ -48,6 +48,8 @@ class CMedium(C.Structure):
 
 SIGS = {
     "fw25_mapgen": (C.c_int, [C.POINTER(CMedium), C.c_int32, C.POINTER(C.c_void_p), _D]),
+    "fw25_mapgen_slab": (C.c_int, [C.POINTER(CMedium), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                   C.POINTER(C.c_void_p), _D]),
     "fw25_mapset_problem": (C.c_int, [C.c_void_p, C.POINTER(engine.CProblem)]),
     "fw25_mapset_read": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p]),
     "fw25_mapset_invalid_count": (C.c_int64, [C.c_void_p]),
@@ -95,6 +97,9 @@ class MediumSpec:
     theoretical_reflection_coefficient: float = 1e-30
     dcmap_full3d: bool = False
     extra: dict = field(default_factory=dict)
+    # x-sharded runs: the maps hold only the user-grid x planes [u0, u0 + n) of a grid whose full extent is user_shape
+    # (each rank keeps the planes its slab reads); extra must then carry c_min / c_max of the WHOLE medium
+    user_planes: tuple | None = None
 
     @property
     def ndim(self) -> int:
@@ -189,7 +194,10 @@ def marshal_medium(spec: MediumSpec):
     (fw25_medium.input_f32) when EVERY user-grid map is float32; otherwise everything is float64."""
     if spec.ndim not in (2, 3):
         raise ValueError("the medium must be 2D or 3D")
-    shape = tuple(int(n) for n in spec.user_shape)
+    full_shape = tuple(int(n) for n in spec.user_shape)
+    shape = full_shape if spec.user_planes is None else (int(spec.user_planes[1]),) + full_shape[1:]
+    if spec.user_planes is not None and not ("c_min" in spec.extra and "c_max" in spec.extra):
+        raise ValueError("a MediumSpec holding a plane range needs extra['c_min'] / extra['c_max'] of the whole medium")
     md = CMedium()
     keep = []
     user = [spec.sound_speed, spec.density, spec.beta]
@@ -207,7 +215,7 @@ def marshal_medium(spec: MediumSpec):
         return a.ctypes.data
 
     md.ndim = spec.ndim
-    md.nx, md.ny, md.nz = shape[0], shape[1], shape[2] if spec.ndim == 3 else 1
+    md.nx, md.ny, md.nz = full_shape[0], full_shape[1], full_shape[2] if spec.ndim == 3 else 1
     md.m_spatial_order, md.n_pml_layer = spec.m_spatial_order, spec.n_pml_layer
     md.n_transition_layer, md.use_pml = spec.n_transition_layer, int(spec.use_pml)
     md.dt = spec.dt
@@ -273,17 +281,25 @@ def run_medium(spec: MediumSpec, pb, device: int = 0):
 class MapSet:
     """Device-resident maps of one medium (fw25_mapset).  Keep it alive as long as an engine uses it."""
 
-    def __init__(self, spec: MediumSpec, device: int = 0):
+    def __init__(self, spec: MediumSpec, device: int = 0, planes: tuple | None = None):
+        """planes = (gx0, gx1): build the extended x planes [gx0, gx1) only (one x-slab incl. its ghost planes,
+        fw25_mapgen_slab); spec.user_planes says which user-grid planes the host arrays hold."""
         self.spec = spec
         self.device = device
         md, keep, (self.d_table, self.dmap, self.ndmap) = marshal_medium(spec)
         h = C.c_void_p()
         ms = (C.c_double * 2)()
-        engine._check(_lib().fw25_mapgen(C.byref(md), device, C.byref(h), ms))
+        if planes is None and spec.user_planes is None:
+            engine._check(_lib().fw25_mapgen(C.byref(md), device, C.byref(h), ms))
+            self.shape = spec.extended_shape
+        else:
+            gx0, gx1 = planes if planes is not None else (0, spec.extended_shape[0])
+            u0, un = spec.user_planes if spec.user_planes is not None else (0, spec.user_shape[0])
+            engine._check(_lib().fw25_mapgen_slab(C.byref(md), device, int(gx0), int(gx1), int(u0), int(un), C.byref(h), ms))
+            self.shape = (int(gx1) - int(gx0),) + tuple(spec.extended_shape[1:])
         del keep
         self._h = h
         self.upload_ms, self.kernel_ms = ms[0], ms[1]
-        self.shape = spec.extended_shape
         self.invalid_count = int(_lib().fw25_mapset_invalid_count(h))
 
     def fill(self, cpb: "engine.CProblem") -> None:

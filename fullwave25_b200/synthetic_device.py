@@ -173,24 +173,28 @@ def maps_to_host(maps: dict, nZ: int, pin: bool = True) -> dict:
     return out
 
 
-def make_user_medium(user_shape, *, device, block: int = 24, seed: int = 1234, pin: bool = True, chunk: int = 16):
+def make_user_medium(user_shape, *, device, block: int = 24, seed: int = 1234, pin: bool = True, chunk: int = 16,
+                     x_range: tuple | None = None):
     """The synthetic tissue medium as a USER-grid `fullwave.Medium` would hold it -- sound_speed, density, beta,
     alpha_coeff, alpha_power -- as float32 HOST arrays (pinned), generated on the device chunk by chunk.  Input of the
-    GPU map builder (`mapgen.MediumSpec` with a look-up table).  Returns (maps, c_min, c_max)."""
+    GPU map builder (`mapgen.MediumSpec` with a look-up table).  x_range = (x0, x1): only those x planes of the grid
+    (a rank of an x-sharded run keeps the planes its slab reads; labels hash the GLOBAL block coordinates).
+    Returns (maps, c_min, c_max, pinned tensors) -- c_min / c_max over the planes generated."""
     import torch
 
     nx, ny, nz = (int(s) for s in user_shape)
+    x_lo, x_hi = (0, nx) if x_range is None else (int(x_range[0]), int(x_range[1]))
     dev = torch.device(device)
     f32 = torch.float32
     tis = torch.tensor(synthetic.TISSUES, dtype=f32, device=dev)
     ntis = tis.shape[0]
     names = ("sound_speed", "density", "beta", "alpha_coeff", "alpha_power")
-    host = {n: torch.empty((nx, ny, nz), dtype=f32, pin_memory=pin) for n in names}
+    host = {n: torch.empty((x_hi - x_lo, ny, nz), dtype=f32, pin_memory=pin) for n in names}
     by = (torch.arange(ny, device=dev) // block).to(torch.int64)
     bz = (torch.arange(nz, device=dev) // block).to(torch.int64)
     c_min, c_max = float("inf"), float("-inf")
-    for x0 in range(0, nx, chunk):
-        x1 = min(x0 + chunk, nx)
+    for x0 in range(x_lo, x_hi, chunk):
+        x1 = min(x0 + chunk, x_hi)
         gx = torch.arange(x0, x1, device=dev)
         bx = (gx // block).to(torch.int64)
         h = (bx[:, None, None] * 73856093) ^ (by[None, :, None] * 19349663) ^ (bz[None, None, :] * 83492791) ^ (seed * 2654435761)
@@ -201,7 +205,7 @@ def make_user_medium(user_shape, *, device, block: int = 24, seed: int = 1234, p
         c = tis[lab, 0] + (jit.to(f32) / 65535.0 - 0.5) * 0.8
         c_min, c_max = min(c_min, float(c.min())), max(c_max, float(c.max()))
         for n, v in zip(names, (c, tis[lab, 1], tis[lab, 2], tis[lab, 3], tis[lab, 4])):
-            host[n][x0:x1].copy_(v, non_blocking=True)
+            host[n][x0 - x_lo:x1 - x_lo].copy_(v, non_blocking=True)
         torch.cuda.synchronize(dev)
         del h, lab, jit, c
     return {n: t.numpy() for n, t in host.items()}, c_min, c_max, host

@@ -213,7 +213,14 @@ typedef struct fw25_mapset fw25_mapset; /* opaque: the 13 float maps + dcmap, de
 /* Builds the maps on `device`.  stats_ms (may be NULL): [0] = host->device upload of the user-grid maps,
  * [1] = the kernel (CUDA events). */
 int fw25_mapgen(const fw25_medium *md, int32_t device, fw25_mapset **out, double *stats_ms);
-/* Fills nX nY nZ (the EXTENDED grid), the 13 map pointers, dcmap, maps_on_device, map_pitch and dcmap_full3d of `pb`
+/* One x-slab of the same maps: extended planes [gx0, gx1) only (a rank of an x-sharded run builds its own planes, ghost
+ * planes included -- the reference's binary uploads whole maps and slices them per GPU, ASM 0x405f78-0x406204).  `md`
+ * describes the WHOLE user grid (nx = its full extent), but its map pointers address host arrays that hold only the
+ * user-grid planes [u_plane0, u_plane0 + u_planes); they must cover clamp(gx0 - nb) .. clamp(gx1 - 1 - nb), nb =
+ * m_spatial_order + n_pml_layer + n_transition_layer.  The values are those fw25_mapgen gives the same planes. */
+int fw25_mapgen_slab(const fw25_medium *md, int32_t device, int32_t gx0, int32_t gx1, int32_t u_plane0, int32_t u_planes,
+                     fw25_mapset **out, double *stats_ms);
+/* Fills nX nY nZ (the EXTENDED grid; nX = the planes held, for a slab), the 13 map pointers, dcmap, maps_on_device, map_pitch and dcmap_full3d of `pb`
  * so that fw25_create adopts the maps without a copy.  The mapset must outlive every engine created from it. */
 int fw25_mapset_problem(const fw25_mapset *ms, fw25_problem *pb);
 /* name: a .dat stem ("rho", "K", "beta", "kappax", ..., "bpmlu2", "dcmap"); out: dense [nX][nY][nZ] float32 (int32

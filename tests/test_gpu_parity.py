@@ -243,6 +243,31 @@ def test_anisotropic_3d_on_the_warp_specialised_sweeps(built_lib, variant):
     assert np.abs(want_g).max() > 0
 
 
+@pytest.mark.parametrize("variant", [0, 1, 2])
+def test_anisotropic_2d_on_the_tiled_sweeps(built_lib, variant):
+    """2D per-axis maps: the TMA-tiled one-cell-per-thread sweeps (k_sweep_*_2dc<2, .., ANISO = true>, default and
+    variant 2) and the L1/L2-path kernels (variant 1) equal the oracle and the reference's anisotropic 2D binary
+    (tests/golden/ref_aniso2d.npz), also on a ragged grid of several column tiles, with graph replay on and off."""
+    from fullwave25_b200 import synthetic
+    from tests.test_oracle_golden import load_golden
+    pb = cases.make("aniso2d")
+    with engine.Engine(pb, variant=variant) as e:
+        e.step(pb.nT)
+        e.sync()
+        np.testing.assert_array_equal(e.read_frames(0, pb.n_frames), load_golden("aniso2d"))
+    big = synthetic.make_problem((147, 301), nT=90, modT=3, seed=25, aniso=True, n_air=0, n_sensors=300)
+    want_g, want = oracle.run(big, return_fields=True)
+    with engine.Engine(big, variant=variant) as e:
+        e.step(big.nT)
+        e.sync()
+        for k in "puv":
+            np.testing.assert_array_equal(e.field(k), want[k], err_msg=k)
+        np.testing.assert_array_equal(e.read_frames(0, big.n_frames), want_g)
+    got, _ = engine.run(big)                       # the whole-job path (graph-replayed steps)
+    np.testing.assert_array_equal(got, want_g)
+    assert np.abs(want_g).max() > 0
+
+
 @pytest.mark.parametrize("fused", ["1", "0"])
 def test_anisotropic_3d_on_two_slabs(built_lib, fused, monkeypatch):
     """The anisotropic family sharded over two x-slabs (fw25_run with a device list; both slabs on device 0 when the

@@ -48,6 +48,50 @@ def test_reference_3d_dcmap_truncation_is_applied_on_request():
     assert np.array_equal(dc.reshape(-1), full) and full.any()
 
 
+@pytest.mark.parametrize("name", ["m3d_big", "m2d_big", "m3d_lut", "m3d_onecell"])
+def test_slab_maps_equal_the_planes_of_the_whole_grid(name):
+    """fw25_mapgen_slab: an x-slab's planes (ghost planes included), built from host arrays that hold only the user-grid
+    planes the slab reads, are byte-identical to the same planes of fw25_mapgen -- in the per-voxel and in the reference
+    3D binary's dcmap mode, for first / interior / last slabs and a slab that lies wholly inside the boundary layer."""
+    import dataclasses
+    g = np.load(GOLD / f"mapgen_{name}.npz")
+    for full3d in (True, False):
+        spec = spec_of(name, g)
+        spec.dcmap_full3d = full3d
+        c = np.asarray(spec.sound_speed)
+        spec.extra.update(c_min=float(c.min()), c_max=float(c.max()))
+        nb, ex, ux = spec.num_boundary_points, spec.extended_shape[0], spec.user_shape[0]
+        with mapgen.MapSet(spec) as whole:
+            want = device_maps_of(whole)
+        cuts = sorted({0, min(3, ex - 1), nb // 2 + 1, ex // 2, max(ex - nb + 2, 1), ex})
+        for gx0, gx1 in zip(cuts[:-1], cuts[1:]):
+            lo, hi = max(gx0 - 8, 0), min(gx1 + 8, ex)                      # owned planes + 8 ghost planes per side
+            u0 = min(max(lo - nb, 0), ux - 1)
+            u1 = min(max(hi - 1 - nb, 0), ux - 1) + 1
+
+            def cut(a):
+                return np.ascontiguousarray(np.asarray(a)[u0:u1])
+            part = dataclasses.replace(
+                spec, sound_speed=cut(spec.sound_speed), density=cut(spec.density), beta=cut(spec.beta),
+                relax=None if spec.relax is None else {k: cut(v) for k, v in spec.relax.items()},
+                alpha_coeff=None if spec.alpha_coeff is None else cut(spec.alpha_coeff),
+                alpha_power=None if spec.alpha_power is None else cut(spec.alpha_power), user_planes=(u0, u1 - u0))
+            with mapgen.MapSet(part, planes=(lo, hi)) as ms:
+                assert ms.shape == (hi - lo,) + tuple(spec.extended_shape[1:])
+                got = device_maps_of(ms)
+                assert ms.invalid_count >= 0
+            for stem in MAP_NAMES + ("dcmap",):
+                assert np.array_equal(got[stem], want[stem][lo:hi]), (stem, lo, hi, full3d)
+    if ux > 1:           # host arrays that lack planes the slab reads are refused
+        one = lambda a: None if a is None else np.ascontiguousarray(np.asarray(a)[:1])   # noqa: E731
+        short = dataclasses.replace(
+            spec, sound_speed=one(spec.sound_speed), density=one(spec.density), beta=one(spec.beta),
+            relax=None if spec.relax is None else {k: one(v) for k, v in spec.relax.items()},
+            alpha_coeff=one(spec.alpha_coeff), alpha_power=one(spec.alpha_power), user_planes=(0, 1))
+        with pytest.raises(engine.EngineError, match="do not hold the user-grid planes"):
+            mapgen.MapSet(short, planes=(0, ex))
+
+
 def test_lookup_counts_invalid_entries():
     g = np.load(GOLD / "mapgen_m2d_lut.npz")
     spec = spec_of("m2d_lut", g)
