@@ -568,7 +568,10 @@ int pick_chunk_ws(const Geom &G, int planes) {
   (void)G;
   static const int lx_env = [] { const char *e = getenv("FW25_WS_LX"); return e ? atoi(e) : 0; }();
   const int target = lx_env > 0 ? lx_env : 32;
-  const int chunks = (planes + target - 1) / target;
+  int chunks = (planes + target - 1) / target;
+  // short launches (the interior of a 100-plane slab is 36 planes): one 36-plane chunk instead of two of 18, whose 15
+  // prologue planes each would nearly double the column loads
+  if (lx_env <= 0 && chunks > 1 && planes / chunks < 24) --chunks;
   return (planes + chunks - 1) / chunks;
 }
 

@@ -206,6 +206,7 @@ def make_user_medium(user_shape, *, device, block: int = 24, seed: int = 1234, p
         c_min, c_max = min(c_min, float(c.min())), max(c_max, float(c.max()))
         for n, v in zip(names, (c, tis[lab, 1], tis[lab, 2], tis[lab, 3], tis[lab, 4])):
             host[n][x0 - x_lo:x1 - x_lo].copy_(v, non_blocking=True)
-        torch.cuda.synchronize(dev)
+        if dev.type == "cuda":
+            torch.cuda.synchronize(dev)
         del h, lab, jit, c
     return {n: t.numpy() for n, t in host.items()}, c_min, c_max, host

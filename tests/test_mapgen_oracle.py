@@ -153,3 +153,37 @@ def test_spec_from_a_medium_with_lookup_database(tmp_path):
     np.testing.assert_array_equal(spec.lut.alpha_list, lut["alpha_list"])
     np.testing.assert_array_equal(spec.lut.power_list, lut["power_list"])
     assert spec.lut.invalid_matrix.shape == lut["invalid_matrix"].shape and spec.lut.invalid_matrix[-1, -1]
+
+
+def test_plane_range_specs_marshal_with_the_whole_grid_extent():
+    """x-sharded runs: a MediumSpec that holds only a range of user-grid x planes (fw25_mapgen_slab) keeps the WHOLE
+    grid's extent in fw25_medium.nx, checks its arrays against the plane count, and needs the global sound-speed range
+    (the stencil table must be the same on every rank)."""
+    import dataclasses
+    spec = spec_of("m3d_big")
+    cut = lambda a: np.ascontiguousarray(np.asarray(a)[5:12])   # noqa: E731
+    part = dataclasses.replace(spec, sound_speed=cut(spec.sound_speed), density=cut(spec.density), beta=cut(spec.beta),
+                               relax={k: cut(v) for k, v in spec.relax.items()}, user_planes=(5, 7))
+    with pytest.raises(ValueError, match="c_min"):
+        mapgen.marshal_medium(part)
+    c = np.asarray(spec.sound_speed)
+    part.extra.update(c_min=float(c.min()), c_max=float(c.max()))
+    md, keep, tables = mapgen.marshal_medium(part)
+    whole_md, _, whole_tables = mapgen.marshal_medium(spec)
+    assert (md.nx, md.ny, md.nz) == (whole_md.nx, whole_md.ny, whole_md.nz) == tuple(spec.user_shape)
+    assert md.c_round_min == whole_md.c_round_min and tables[2] == whole_tables[2]
+    np.testing.assert_array_equal(tables[1], whole_tables[1])
+    with pytest.raises(ValueError, match="map shape error"):
+        mapgen.marshal_medium(dataclasses.replace(part, user_planes=(5, 8)))
+
+
+def test_user_medium_generator_plane_ranges_equal_the_whole_medium():
+    """bench.py's per-rank user-grid medium (synthetic_device.make_user_medium(x_range=...)) is the same medium as the
+    whole one: labels hash GLOBAL block coordinates."""
+    from fullwave25_b200 import synthetic_device
+    whole, c0, c1, _ = synthetic_device.make_user_medium((40, 12, 10), device="cpu", block=6, seed=9, pin=False)
+    part, p0, p1, _ = synthetic_device.make_user_medium((40, 12, 10), device="cpu", block=6, seed=9, pin=False,
+                                                        x_range=(13, 31), chunk=7)
+    for k in whole:
+        np.testing.assert_array_equal(part[k], whole[k][13:31])
+    assert c0 <= p0 <= p1 <= c1
