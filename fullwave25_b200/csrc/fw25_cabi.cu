@@ -20,6 +20,7 @@ int32_t fw25_pitch(int32_t n_fast) { return fw25::round_up(n_fast, 32); }
 int fw25_create(const fw25_problem *pb, const fw25_slab *slab, int32_t device, fw25_engine **out) {
   if (!pb || !out) { g_err = "fw25_create: NULL argument"; return 1; }
   *out = nullptr;
+  fw25::reap_wait();                         // a previous whole-job call may still be giving its memory back
   std::unique_ptr<fw25_engine> h(new fw25_engine());
   try {
     h->e.init(*pb, slab, device);

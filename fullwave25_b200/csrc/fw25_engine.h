@@ -47,6 +47,10 @@ inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 bool detect_box(const int32_t *c, int n, int nd, int32_t *box);
 
+// deferred teardown of whole-job runs (fw25_run.cu): one reaper thread; allocating entry points join it first
+void reap_wait();
+void reap_async(std::function<void()> fn);
+
 struct Engine {
   int device = 0;
   int ndim = 3;

@@ -38,6 +38,7 @@
 
 namespace fw25 {
 extern thread_local std::string g_err;
+void reap_wait();   // fw25_run.cu: joins the deferred teardown of a previous whole-job call
 
 namespace {
 
@@ -515,6 +516,7 @@ struct MapStream {
 };
 
 MapStream *mapstream_start(const fw25_medium *md, int device, int block_planes, fw25_mapset **ms_out) {
+  reap_wait();
   std::unique_ptr<MapStream> S(new MapStream());
   try {
     S->start(md, device, block_planes);
@@ -549,6 +551,7 @@ static int mapgen_impl(const fw25_medium *md, int32_t device, int gx0, int gx1, 
                        fw25_mapset **out, double *stats_ms) {
   if (!md || !out) { g_err = "fw25_mapgen: NULL argument"; return 1; }
   *out = nullptr;
+  fw25::reap_wait();                         // a previous whole-job call may still be giving its memory back
   MapgenPlan plan;
   void *scratch = nullptr;   // device scratch: the user-grid inputs
   cudaStream_t st = nullptr;

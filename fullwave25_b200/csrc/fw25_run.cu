@@ -233,10 +233,41 @@ void run_loop(Engine &e, float *genout, fw25_stats *stats, double setup_ms) {
   }
 }
 
+// ---- deferred teardown.  Giving 150 GB of device memory back takes the driver 50-300 ms (unmapping the page tables;
+// profiles/README.md), as long as six time steps of the largest grid.  The whole-job entry points therefore return as
+// soon as the frames are on the host and hand the engine / map set to one reaper thread; every entry point that
+// allocates device memory joins it first (reap_wait), so the memory is back before anybody can miss it, and the
+// library joins it at unload.  FW25_ASYNC_TEARDOWN=0 frees before returning.
+namespace {
+struct Reaper {
+  std::mutex m;
+  std::thread th;
+  void wait() {
+    std::lock_guard<std::mutex> lk(m);
+    if (th.joinable()) th.join();
+  }
+  void run(std::function<void()> fn) {
+    static const bool on = [] { const char *e = getenv("FW25_ASYNC_TEARDOWN"); return !e || atoi(e) != 0; }();
+    if (!on) { fn(); return; }
+    std::lock_guard<std::mutex> lk(m);
+    if (th.joinable()) th.join();
+    th = std::thread(std::move(fn));
+  }
+  ~Reaper() { if (th.joinable()) th.join(); }
+} g_reaper;
+}  // namespace
+
+void reap_wait() { g_reaper.wait(); }
+void reap_async(std::function<void()> fn) { g_reaper.run(std::move(fn)); }
+
 int run_single(const fw25_problem *pb, int dev0, float *genout, fw25_stats *stats) {
   struct Holder {
     fw25_engine *h = nullptr;
-    ~Holder() { if (h) fw25_destroy(h); }
+    ~Holder() {
+      if (!h) return;
+      fw25_engine *e = h;
+      reap_async([e] { fw25_destroy(e); });
+    }
   } H;
   using clk = std::chrono::steady_clock;
   const auto t0 = clk::now();
