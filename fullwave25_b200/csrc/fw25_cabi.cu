@@ -152,11 +152,12 @@ int fw25_run(const fw25_problem *pb, const int32_t *device_ids, int32_t n_device
   }
 }
 
-int fw25_run_medium(const fw25_medium *md, const fw25_problem *pb, int32_t device, float *genout, size_t genout_len,
-                    fw25_stats *stats) {
+static int run_medium_checked(const fw25_medium *md, const fw25_problem *pb, const int32_t *device_ids, int32_t n_devices,
+                              float *genout, size_t genout_len, fw25_stats *stats) {
   if (!md || !pb) { g_err = "fw25_run_medium: NULL argument"; return 1; }
   if (pb->modT <= 0) { g_err = "modT must be >= 1"; return 1; }
   if (pb->aniso) { g_err = "fw25_run_medium: the GPU map builder produces the isotropic file set"; return 1; }
+  if (n_devices < 1 || !device_ids) { g_err = "fw25_run_medium: at least one device id is needed"; return 1; }
   const int n_frames = n_frames_of(pb);
   if (genout_len < (size_t)n_frames * (size_t)std::max(pb->ncoordsout, 0)) {
     g_err = "fw25_run_medium: genout buffer too small";
@@ -164,13 +165,24 @@ int fw25_run_medium(const fw25_medium *md, const fw25_problem *pb, int32_t devic
   }
   if ((size_t)n_frames * std::max(pb->ncoordsout, 0) > 0 && !genout) { g_err = "fw25_run_medium: NULL genout"; return 1; }
   try {
-    return fw25::run_medium(md, pb, device, genout, stats);
+    if (n_devices > 1) return fw25::run_medium_multi(md, pb, device_ids, n_devices, genout, stats);
+    return fw25::run_medium(md, pb, device_ids[0], genout, stats);
   } catch (const Fail &f) {
     return f.code;
   } catch (const std::exception &ex) {
     g_err = std::string("exception: ") + ex.what();
     return 3;
   }
+}
+
+int fw25_run_medium(const fw25_medium *md, const fw25_problem *pb, int32_t device, float *genout, size_t genout_len,
+                    fw25_stats *stats) {
+  return run_medium_checked(md, pb, &device, 1, genout, genout_len, stats);
+}
+
+int fw25_run_medium_multi(const fw25_medium *md, const fw25_problem *pb, const int32_t *device_ids, int32_t n_devices,
+                          float *genout, size_t genout_len, fw25_stats *stats) {
+  return run_medium_checked(md, pb, device_ids, n_devices, genout, genout_len, stats);
 }
 
 int fw25_reset(fw25_engine *h, int32_t nT, int32_t nTic, int32_t ncoords, const int32_t *icc, const float *icmat) {

@@ -333,10 +333,14 @@ int n_frames_of(const fw25_problem *pb);
 void scatter_frames(Engine &e, int f0, int f1, float *genout, int ncoordsout, std::vector<float> &tmp);
 // whole jobs (fw25_run): one engine / one slab per device of this process
 int run_single(const fw25_problem *pb, int dev0, float *genout, fw25_stats *stats);
-int run_multi(const fw25_problem *pb, const int32_t *device_ids, int n, float *genout, fw25_stats *stats);
+// mapsets (optional): per-slab device-resident map sets (fw25_mapgen_slab) adopted instead of pb's host maps
+int run_multi(const fw25_problem *pb, const int32_t *device_ids, int n, float *genout, fw25_stats *stats,
+              fw25_mapset *const *mapsets = nullptr);
 // the time loop over an existing engine, from its current step to nT (fw25_run_engine)
 void run_loop(Engine &e, float *genout, fw25_stats *stats, double setup_ms);
 // fw25_mapgen + fw25_run pipelined (fw25_pipeline.cu)
 int run_medium(const fw25_medium *md, const fw25_problem *pb, int device, float *genout, fw25_stats *stats);
+int run_medium_multi(const fw25_medium *md, const fw25_problem *pb, const int32_t *device_ids, int n, float *genout,
+                     fw25_stats *stats);
 
 }  // namespace fw25

@@ -42,7 +42,9 @@ struct MultiRun {
     }
   }
 
-  void init(const fw25_problem &pb, const int32_t *device_ids, int n) {
+  // mapsets (optional): one device-resident map set per slab, planes [gx0, gx1) of that slab (fw25_mapgen_slab) --
+  // adopted in place instead of slicing and uploading pb's host maps
+  void init(const fw25_problem &pb, const int32_t *device_ids, int n, fw25_mapset *const *mapsets = nullptr) {
     const int nX = pb.nX, base = nX / n, rem = nX % n;
     if (base < 2 * M) fw25::fail(1, "x-slabs would be thinner than two halos (16 planes): use fewer GPUs");
     if (pb.ext_p || pb.ext_u || pb.ext_v || pb.ext_w) fw25::fail(1, "caller-owned state arrays need a single device");
@@ -62,14 +64,18 @@ struct MultiRun {
       lo = x.own_hi;
       fw25_problem sub = pb;
       sub.nX = x.gx1 - x.gx0;
-      const size_t off = (size_t)x.gx0 * row;
+      const size_t off = mapsets ? 0 : (size_t)x.gx0 * row;
+      if (mapsets) {
+        if (fw25_mapset_problem(mapsets[r], &sub) != 0) throw Fail{1};
+        if (sub.nX != x.gx1 - x.gx0) fw25::fail(1, "a per-slab map set does not hold the slab's planes");
+      }
       const float **maps[13] = {&sub.rho, &sub.K, &sub.beta, &sub.kappax, &sub.kappau, &sub.apmlx1, &sub.bpmlx1,
                                 &sub.apmlx2, &sub.bpmlx2, &sub.apmlu1, &sub.bpmlu1, &sub.apmlu2, &sub.bpmlu2};
       for (auto m : maps)
         if (*m) *m += off;
       if (sub.dcmap) sub.dcmap += off;
       fw25_aniso an_sub;
-      if (pb.aniso) {
+      if (pb.aniso && !mapsets) {
         an_sub = *pb.aniso;
         for (int ax = 0; ax < 3; ++ax) {
           if (an_sub.kappa_vel[ax]) an_sub.kappa_vel[ax] += off;
@@ -354,12 +360,13 @@ struct MultiRun {
 
 }  // namespace
 
-int run_multi(const fw25_problem *pb, const int32_t *device_ids, int n, float *genout, fw25_stats *stats) {
+int run_multi(const fw25_problem *pb, const int32_t *device_ids, int n, float *genout, fw25_stats *stats,
+              fw25_mapset *const *mapsets) {
   using clk = std::chrono::steady_clock;
   auto ms_since = [](clk::time_point a) { return std::chrono::duration<double, std::milli>(clk::now() - a).count(); };
   MultiRun mr;
   const auto t0 = clk::now();
-  mr.init(*pb, device_ids, n);
+  mr.init(*pb, device_ids, n, mapsets);
   mr.sync_all();
   const double setup_ms = ms_since(t0);
   const int n_frames = n_frames_of(pb);
@@ -401,6 +408,50 @@ int run_multi(const fw25_problem *pb, const int32_t *device_ids, int n, float *g
     stats->n_devices = n;
   }
   return 0;
+}
+
+// fw25_run_medium on several devices: every device builds its own x-slab of the maps (fw25_mapgen_slab, all devices at
+// once, one host thread each) from the user-grid medium, the slabs are adopted in place and the native multi-device
+// runner steps them.  The partition is MultiRun::init's (the reference's rule).
+int run_medium_multi(const fw25_medium *md, const fw25_problem *pb_in, const int32_t *device_ids, int n, float *genout,
+                     fw25_stats *stats) {
+  using clk = std::chrono::steady_clock;
+  const auto t0 = clk::now();
+  const int nb = md->m_spatial_order + md->n_pml_layer + md->n_transition_layer;
+  const int nX = md->nx + 2 * nb, base = nX / n, rem = nX % n;
+  if (base < 2 * M) fw25::fail(1, "x-slabs would be thinner than two halos (16 planes): use fewer GPUs");
+  struct Sets {
+    std::vector<fw25_mapset *> ms;
+    ~Sets() { for (auto *m : ms) if (m) fw25_mapset_destroy(m); }
+  } S;
+  S.ms.assign(n, nullptr);
+  std::vector<std::string> errs(n);
+  std::vector<int> rcs(n, 0);
+  std::vector<double> gen_ms((size_t)2 * n, 0.0);
+  {
+    std::vector<std::thread> th;
+    int lo = 0;
+    for (int r = 0; r < n; ++r) {
+      const int own_hi = lo + base + (r < rem ? 1 : 0);
+      const int gx0 = r > 0 ? lo - M : 0, gx1 = r < n - 1 ? own_hi + M : nX;
+      lo = own_hi;
+      th.emplace_back([&, r, gx0, gx1] {
+        rcs[r] = fw25_mapgen_slab(md, device_ids[r], gx0, gx1, 0, md->nx, &S.ms[r], &gen_ms[2 * r]);
+        if (rcs[r]) errs[r] = fw25_last_error();          // g_err is thread-local
+      });
+    }
+    for (auto &t : th) t.join();
+  }
+  for (int r = 0; r < n; ++r)
+    if (rcs[r]) { g_err = errs[r]; throw Fail{rcs[r]}; }
+  const double mapgen_wall_ms = std::chrono::duration<double, std::milli>(clk::now() - t0).count();
+  fw25_problem pb = *pb_in;
+  pb.ndim = md->ndim;
+  pb.nX = nX; pb.nY = md->ny + 2 * nb; pb.nZ = md->ndim == 3 ? md->nz + 2 * nb : 1;
+  pb.aniso = nullptr;
+  const int rc = run_multi(&pb, device_ids, n, genout, stats, S.ms.data());
+  if (stats) stats->setup_ms += mapgen_wall_ms;
+  return rc;
 }
 
 }  // namespace fw25

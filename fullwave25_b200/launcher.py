@@ -404,6 +404,26 @@ def _run_solver_device_maps(solver, sensor, out_box, device: int, session: Sessi
     return genout, stats, pb
 
 
+def _run_solver_device_maps_multi(solver, sensor, out_box, device_ids):
+    """maps="device" on several GPUs: no `PMLBuilder.run`, no extended-grid array on the host, and no single device
+    ever holds the whole grid -- `mapgen.run_medium(device_ids=...)` (fw25_run_medium_multi)."""
+    from types import SimpleNamespace
+
+    from . import mapgen
+    pmlb = solver.pml_builder
+    t0 = time.perf_counter()
+    spec = mapgen.MediumSpec.from_pml_builder(pmlb, use_pml=solver.use_pml, dcmap_full3d=False)
+    d_table, dmap, ndmap, _ = spec.stencil_tables()
+    source, _, icczero = lean_lists(pmlb)
+    if not getattr(solver, "use_isotropic_relaxation", True):
+        icczero = icczero[:0]
+    shape_only = SimpleNamespace(shape=spec.extended_shape, ndmap=ndmap, dmap=dmap, d_table=d_table)
+    pb = Problem.for_device_maps(shape_only, pmlb.extended_grid, source, sensor, out_box=out_box, icczero=icczero)
+    genout, stats = mapgen.run_medium(spec, pb, device_ids=device_ids)
+    stats.update(host_setup_s=time.perf_counter() - t0 - stats["native_call_ms"] / 1e3, maps="device")
+    return genout, stats, pb
+
+
 def _remember(stats: dict) -> None:
     global last_run_stats
     last_run_stats = dict(stats)
@@ -427,6 +447,18 @@ def run_solver(solver, *, record_whole_domain: bool = False, sampling_modulus_ti
             release()             # an engine kept for static-map reuse would only be in the way
         try:
             genout, stats, pb = _run_solver_device_maps(solver, sensor, out_box, ids[0], session)
+        except (engine.EngineError, ValueError) as e:
+            raise _sim_error(str(e)) from e
+        result = genout.reshape(-1, pb.ncoordsout).T
+        _remember(stats)
+        return (result, stats) if return_stats else result
+    if maps == "device" and len(ids) > 1 and session is None:
+        # several GPUs: every device builds its own x-slab of the maps from the user-grid medium (fw25_run_medium_multi)
+        from . import mapgen
+        sensor, out_box = _sensor_and_box(solver, record_whole_domain, sampling_modulus_time_whole_domain, lean=True)
+        release()
+        try:
+            genout, stats, pb = _run_solver_device_maps_multi(solver, sensor, out_box, ids)
         except (engine.EngineError, ValueError) as e:
             raise _sim_error(str(e)) from e
         result = genout.reshape(-1, pb.ncoordsout).T

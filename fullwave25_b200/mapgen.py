@@ -56,6 +56,8 @@ SIGS = {
     "fw25_mapset_destroy": (None, [C.c_void_p]),
     "fw25_run_medium": (C.c_int, [C.POINTER(CMedium), C.POINTER(engine.CProblem), C.c_int32, engine._F, C.c_size_t,
                                   C.POINTER(engine.CStats)]),
+    "fw25_run_medium_multi": (C.c_int, [C.POINTER(CMedium), C.POINTER(engine.CProblem), engine._I, C.c_int32, engine._F,
+                                        C.c_size_t, C.POINTER(engine.CStats)]),
 }
 
 
@@ -254,11 +256,12 @@ def marshal_medium(spec: MediumSpec):
     return md, keep, tables[:3]
 
 
-def run_medium(spec: MediumSpec, pb, device: int = 0):
+def run_medium(spec: MediumSpec, pb, device: int = 0, device_ids=None):
     """Whole job from the USER-grid medium through fw25_run_medium (C-ABI): the medium is uploaded block by block, the
     maps are generated as the blocks land and the first time steps already run underneath.  pb: a Problem holding the
     step counts and the coordinate lists on the EXTENDED grid (`Problem.for_device_maps`-style; its maps are unused).
-    Returns (genout [n_frames, ncoordsout], stats)."""
+    device_ids with several entries: x-slabs over those GPUs, each building its own slab of the maps
+    (fw25_run_medium_multi).  Returns (genout [n_frames, ncoordsout], stats)."""
     import time
     t0 = time.perf_counter()
     md, keep, (d_table, dmap, ndmap) = marshal_medium(spec)
@@ -269,8 +272,14 @@ def run_medium(spec: MediumSpec, pb, device: int = 0):
     genout = np.zeros((pb.n_frames, pb.ncoordsout), np.float32)
     st = engine.CStats()
     t1 = time.perf_counter()
-    engine._check(_lib().fw25_run_medium(C.byref(md), C.byref(s), device, genout.ctypes.data_as(engine._F), genout.size,
-                                         C.byref(st)))
+    if device_ids is not None and len(device_ids) > 1:
+        ids = np.asarray(list(device_ids), np.int32)
+        engine._check(_lib().fw25_run_medium_multi(C.byref(md), C.byref(s), ids.ctypes.data_as(engine._I), len(ids),
+                                                   genout.ctypes.data_as(engine._F), genout.size, C.byref(st)))
+    else:
+        dev0 = int(device_ids[0]) if device_ids else device
+        engine._check(_lib().fw25_run_medium(C.byref(md), C.byref(s), dev0, genout.ctypes.data_as(engine._F), genout.size,
+                                             C.byref(st)))
     t2 = time.perf_counter()
     del keep, keep2
     stats = {f: getattr(st, f) for f, _ in engine.CStats._fields_}

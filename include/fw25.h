@@ -238,6 +238,11 @@ void fw25_mapset_destroy(fw25_mapset *ms);
  * extended-grid coordinates); its grid sizes and map pointers are ignored (they follow from md).  One device. */
 int fw25_run_medium(const fw25_medium *md, const fw25_problem *pb, int32_t device, float *genout, size_t genout_len,
                     fw25_stats *stats);
+/* The same job x-sharded over several GPUs of this process (`cuda_device_id=[0, 1, ...]`, launcher.py:63-105): every
+ * device builds its own slab of the maps from the user-grid medium (fw25_mapgen_slab, all devices at once) and the
+ * native multi-device runner of fw25_run steps them.  n_devices = 1 is fw25_run_medium. */
+int fw25_run_medium_multi(const fw25_medium *md, const fw25_problem *pb, const int32_t *device_ids, int32_t n_devices,
+                          float *genout, size_t genout_len, fw25_stats *stats);
 
 const char *fw25_last_error(void);
 int32_t fw25_abi_version(void);

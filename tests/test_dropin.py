@@ -168,6 +168,10 @@ def test_run_solver_with_gpu_built_maps_matches_reference_binary(built_lib, shap
             again = launcher.run_solver(s_ref, maps="device", session=ses)     # maps stay resident, sources re-sent
         np.testing.assert_array_equal(first, got)
         np.testing.assert_array_equal(again, got)
+        # a device list: every slab builds its own planes of the maps (fw25_run_medium_multi); same bits as one device
+        two, st2 = launcher.run_solver(s_ref, maps="device", cuda_device_id=[0, 0], return_stats=True)
+        assert st2["n_devices"] == 2 and st2["maps"] == "device"
+        np.testing.assert_array_equal(two, got)
 
 
 @needs_ref

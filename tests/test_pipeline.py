@@ -112,6 +112,25 @@ def test_streamed_maps_equal_one_shot_maps(monkeypatch):
     assert stats2["skewed_steps"] == 2
 
 
+@pytest.mark.parametrize("n,fused", [(2, "1"), (2, "0"), (3, "1")])
+def test_run_medium_on_several_devices(monkeypatch, n, fused):
+    """fw25_run_medium_multi: every device builds its own x-slab of the maps (fw25_mapgen_slab) from the user-grid
+    medium and the native multi-device runner steps them -- the same bits as one device (slabs share device 0 when the
+    box has a single GPU), with sources / sensors / air voxels near the interfaces and in the rim."""
+    from tests.test_multi_gpu import _devices
+    monkeypatch.setenv("FW25_FUSED_HALO", fused)
+    spec, pb = spec_and_problem((112, 24, 30), n_pml=5, n_trans=3, nT=26, modT=3, seed=41)   # extended 144 x 56 x 62
+    want, _ = sequential(spec, pb)
+    got, stats = mapgen.run_medium(spec, pb, device_ids=_devices(n))
+    assert stats["n_devices"] == n and stats["halo_bytes"] > 0 and np.abs(want).max() > 0
+    np.testing.assert_array_equal(got, want)
+    spec.dcmap_full3d = False                       # the reference 3D binary's dcmap truncation follows the GLOBAL index
+    want2, _ = sequential(spec, pb)
+    got2, _ = mapgen.run_medium(spec, pb, device_ids=_devices(n))
+    np.testing.assert_array_equal(got2, want2)
+    assert not np.array_equal(want2, want)
+
+
 def test_run_medium_reports_errors():
     spec, pb = spec_and_problem((37, 18, 19), n_pml=3, n_trans=2, nT=4, modT=1, seed=47)
     pb.icc = pb.icc.copy()
