@@ -78,7 +78,14 @@ void Engine::release_staging() {
 
 void Engine::setup_sources(int ncoords, const int32_t *icc, const float *icmat) {
   const int nd = ndim;
+  const bool trace = getenv("FW25_SETUP_TRACE") != nullptr;
+  const auto ts0 = std::chrono::steady_clock::now();
+  auto tp = [&](const char *what) {
+    if (trace) fprintf(stderr, "[fw25 sources] %-24s +%7.1f ms\n", what,
+                       std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - ts0).count());
+  };
   FW_CUDA(cudaStreamSynchronize(stream));            // the previous lists may still be in flight (reset)
+  tp("stream drained");
   for (void *p : src_owned) cudaFree(p);
   src_owned.clear();
   n_src = n_src_rim = 0;
@@ -94,11 +101,13 @@ void Engine::setup_sources(int ncoords, const int32_t *icc, const float *icmat) 
   std::vector<Part> parts(n_thr);
   // every thread writes its rows in place; slab engines drop the sources of other slabs and compact afterwards
   h_src_idx.resize((size_t)ncoords); h_src_row.resize((size_t)ncoords); h_src_flag.resize((size_t)ncoords);
+  tp("host lists allocated");
   auto work = [&](int k) {
     Part &P = parts[k];
     const int i0 = (int)((long long)ncoords * k / n_thr), i1 = (int)((long long)ncoords * (k + 1) / n_thr);
     P.plane.assign((size_t)nXl, 0);
-    int o = i0;
+    unsigned char *plane = P.plane.data();
+    int o = i0, rim = 0;                               // (counters stay thread-local: the Parts share cache lines)
     for (int i = i0; i < i1; ++i) {
       const int32_t *c = icc + (size_t)i * nd;
       if (!coord_ok(c)) { P.bad = true; return; }
@@ -110,9 +119,10 @@ void Engine::setup_sources(int ncoords, const int32_t *icc, const float *icmat) 
       h_src_row[o] = i;
       h_src_flag[o] = (unsigned char)((r ? 1 : 0) | (dead ? 2 : 0));
       ++o;
-      P.rim += (r && !dead);
-      if (!dead) P.plane[c[0] - gx0] = 1;
+      rim += (r && !dead);
+      if (!dead) plane[c[0] - gx0] = 1;
     }
+    P.rim = rim;
     P.kept = o - i0;
   };
   {
@@ -121,6 +131,7 @@ void Engine::setup_sources(int ncoords, const int32_t *icc, const float *icmat) 
     work(0);
     for (auto &t_ : th) t_.join();
   }
+  tp("coordinates resolved");
   size_t out = 0;
   for (int k = 0; k < n_thr; ++k) {
     Part &P = parts[k];
@@ -137,16 +148,20 @@ void Engine::setup_sources(int ncoords, const int32_t *icc, const float *icmat) 
   }
   h_src_idx.resize(out); h_src_row.resize(out); h_src_flag.resize(out);
   n_src = (int)h_src_idx.size();
+  tp("lists compacted");
   d_src_idx = salloc<long long>(n_src); d_src_row = salloc<int>(n_src); d_src_rim = salloc<unsigned char>(n_src);
   d_icmat = nullptr;
+  tp("device lists allocated");
   if (n_src) {   // the host lists are members: nothing here waits for the copies
     FW_CUDA(cudaMemcpyAsync(d_src_idx, h_src_idx.data(), n_src * sizeof(long long), cudaMemcpyHostToDevice, stream));
     FW_CUDA(cudaMemcpyAsync(d_src_row, h_src_row.data(), n_src * sizeof(int), cudaMemcpyHostToDevice, stream));
     FW_CUDA(cudaMemcpyAsync(d_src_rim, h_src_flag.data(), n_src, cudaMemcpyHostToDevice, stream));
     const size_t nic = (size_t)ncoords * nTic;
     d_icmat = salloc<float>(nic);
+    tp("index lists queued");
     if (nic) FW_CUDA(cudaMemcpyAsync(d_icmat, icmat, nic * 4, cudaMemcpyHostToDevice, stream));
     h2d_bytes += (int64_t)nic * 4;
+    tp("signals queued");
   }
 }
 

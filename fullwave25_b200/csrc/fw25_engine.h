@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <memory>
 #include <numeric>
 #include <string>
 #include <thread>
@@ -45,6 +46,17 @@ struct Fail {
 
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
+// std::vector allocator whose resize() leaves trivially constructible elements uninitialised
+template <class T>
+struct DefaultInit : std::allocator<T> {
+  template <class U> struct rebind { using other = DefaultInit<U>; };
+  template <class U, class... A>
+  void construct(U *p, A &&...a) {
+    if constexpr (sizeof...(A) == 0) ::new (static_cast<void *>(p)) U;
+    else ::new (static_cast<void *>(p)) U(std::forward<A>(a)...);
+  }
+};
+
 bool detect_box(const int32_t *c, int n, int nd, int32_t *box);
 
 // deferred teardown of whole-job runs (fw25_run.cu): one reaper thread; allocating entry points join it first
@@ -74,9 +86,11 @@ struct Engine {
   int n_sens = 0, n_sens_global = 0;
   std::vector<int32_t> sens_ids;             // global outc row of each local sensor (box sensors: filled on demand)
   // fused 2D step (k_sweep_p_2dc<2, true>): host copies of the point lists and the per-tile CSR built from them
-  std::vector<long long> h_src_idx, h_air_idx, h_sens_idx;
-  std::vector<int> h_src_row;
-  std::vector<unsigned char> h_src_flag;
+  // (the source lists are millions of entries that every element of is written right after the resize: no zero-fill)
+  std::vector<long long, DefaultInit<long long>> h_src_idx;
+  std::vector<long long> h_air_idx, h_sens_idx;
+  std::vector<int, DefaultInit<int>> h_src_row;
+  std::vector<unsigned char, DefaultInit<unsigned char>> h_src_flag;
   bool fuse_ok = false;
   Fuse2D fuse{};
   std::vector<void *> fuse_owned;
