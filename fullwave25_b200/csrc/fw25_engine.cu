@@ -221,7 +221,7 @@ void Engine::init(const fw25_problem &pb, const fw25_slab *slab, int dev) {
   const int mp = pb.map_pitch > 0 ? pb.map_pitch : G.nC;
   if (mp < G.nC) fail(1, "map_pitch is smaller than the fastest axis");
   // anisotropic file set: per-axis maps.  When every axis holds the same values (what the reference's Python
-  // layer writes) the isotropic kernels run on the x-axis copy; otherwise the ANISO simple sweeps read all of them.
+  // layer writes) the isotropic kernels run on the x-axis copy; otherwise the ANISO instantiations read all of them.
   const fw25_aniso *an = pb.aniso;
   aniso_protocol = an != nullptr;
   if (an) {

@@ -107,7 +107,7 @@ struct Engine {
   int64_t launches = 0;
   int variant = 0;
   int64_t h2d_bytes = 0;
-  bool aniso = false;            // per-axis relaxation maps that really differ: ANISO simple sweeps only
+  bool aniso = false;            // per-axis relaxation maps that really differ: the ANISO instantiations of the sweeps
   bool aniso_protocol = false;   // the problem came as the anisotropic file set (its binaries ignore air voxels)
 
   // Whole steps replayed from a CUDA graph (small grids are launch-bound: the 2D examples step in ~10 us).  The step

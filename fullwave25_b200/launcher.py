@@ -436,7 +436,7 @@ def run_solver(solver, *, record_whole_domain: bool = False, sampling_modulus_ti
     engine input is assembled in memory (what InputFileWriter would have written, input_file_writer.py:563-881) --
     bit-identical to the reference binary.  maps="device": the coefficient maps are built on the GPU from the
     user-grid medium instead (fw25_mapgen; a / b within one float32 ulp of the reference's files, everything else
-    bit-identical; one device).  The sensor traces come back as [n_sensors, n_frames] exactly like
+    bit-identical; a device list makes every GPU build its own x-slab of the maps).  The sensor traces come back as [n_sensors, n_frames] exactly like
     `Solver._reshape_sensor_data`."""
     if maps not in ("host", "device"):
         raise ValueError('maps must be "host" or "device"')
