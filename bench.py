@@ -572,8 +572,11 @@ def run_e2e_medium_slabs(args, rank, world, dev, comm, streams, barrier, max_ove
     torch.cuda.empty_cache()
     barrier()
     t0 = time.perf_counter()
-    ms = mapgen.MapSet(spec, device=dev.index or 0, planes=(slab.gx0, slab.gx1))
+    # the set's device pointers are final at once: the engine (state arrays, plans, source / sensor lists) is created
+    # while the user-grid planes are still going up block by block and the maps are generated behind them
+    ms = mapgen.MapSet(spec, device=dev.index or 0, planes=(slab.gx0, slab.gx1), background=True)
     eng = SlabEngine(pb, slab, dev, device_maps=ms.device_maps())
+    ms.wait()
     eng.eng.sync()
     t_setup = time.perf_counter() - t0
     drv = SlabDriver(slab, eng, comm, pb.modT, streams=(main, bnd), ndim=3)
@@ -585,8 +588,9 @@ def run_e2e_medium_slabs(args, rank, world, dev, comm, streams, barrier, max_ove
     e2e = {"value": gX * nY * nZ * K / dt_e2e / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d / K,
            "d2h_bytes_per_step": pb.n_frames * eng.eng.n_local_sensors * 4 / K, "seconds": dt_e2e,
            "setup_seconds": t_setup, "mapgen_upload_ms": ms.upload_ms, "mapgen_kernel_ms": ms.kernel_ms,
-           "api": "per rank: fw25_mapgen_slab (C-ABI; this rank's user-grid planes in pinned host memory -> its slab of "
-                  "the engine maps in HBM) + fw25_create on those maps + SlabDriver.step (NCCL halos) + gather_frames",
+           "api": "per rank: fw25_mapgen_slab_begin / _finish (C-ABI; this rank's user-grid planes in pinned host memory -> "
+                  "its slab of the engine maps in HBM, block by block in the background) + fw25_create on those maps "
+                  "meanwhile + SlabDriver.step (NCCL halos) + gather_frames",
            "grid_per_gpu": f"{nXl}x{nY}x{nZ}", "user_grid": "x".join(map(str, user)),
            "user_planes_rank0": [int(u0), int(u1)], "input_dtype": "float32", "launches": int(eng.eng.launches),
            "finite": bool(np.isfinite(out).all()) if out is not None else None,

@@ -414,6 +414,8 @@ struct MapStream {
   double upload_ms = 0, kernel_ms = 0;
   int64_t h2d_bytes = 0;
   cudaEvent_t t_begin = nullptr, t_end = nullptr;
+  int a_first = 0, a_count = 0;            // extended planes built (an x-slab, or the whole grid)
+  int u_plane0 = 0;                        // user-grid plane the host arrays start at
 
   ~MapStream() {
     if (th.joinable()) th.join();
@@ -428,7 +430,9 @@ struct MapStream {
     if (ring) cudaFree(ring);
   }
 
-  void start(const fw25_medium *md, int dev, int block_planes) {
+  // gx0 / gx1 (gx1 < 0: the whole grid): the extended planes to build; u0 / un (un < 0: the whole user grid): the
+  // user-grid planes the host arrays of `md` hold
+  void start(const fw25_medium *md, int dev, int block_planes, int gx0 = 0, int gx1 = -1, int u0 = 0, int un = -1) {
     device = dev;
     block = block_planes;
     MG_CUDA(cudaSetDevice(device));
@@ -437,8 +441,18 @@ struct MapStream {
     int lo_pri = 0, hi_pri = 0;
     MG_CUDA(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
     MG_CUDA(cudaStreamCreateWithPriority(&gen, cudaStreamNonBlocking, hi_pri));
-    plan.create(md, device, up);
-    n_blocks = (plan.P.nA + block - 1) / block;
+    plan.create(md, device, up, gx0, gx1 < 0 ? -1 : gx1 - gx0);
+    a_first = plan.ms->x0;
+    a_count = plan.ms->nX;
+    if (un < 0) { u0 = 0; un = plan.P.uA; }
+    u_plane0 = u0;
+    {
+      int first, last;
+      plan.user_range(a_first, a_first + a_count, first, last);
+      if (first < u0 || last >= u0 + un)
+        mg_fail("fw25_mapgen_slab: the host arrays do not hold the user-grid planes this slab reads");
+    }
+    n_blocks = (a_count + block - 1) / block;
     map_bytes = (size_t)block * plan.user_plane * plan.elem;
     map_bytes = (map_bytes + 255) / 256 * 256;
     slot_bytes = map_bytes * plan.n_user;
@@ -460,7 +474,7 @@ struct MapStream {
       MG_CUDA(cudaSetDevice(device));
       MG_CUDA(cudaEventRecord(t_begin, up));
       for (int b = 0; b < n_blocks; ++b) {
-        const int a_lo = b * block, a_hi = std::min(a_lo + block, plan.P.nA);
+        const int a_lo = a_first + b * block, a_hi = std::min(a_lo + block, a_first + a_count);
         int u0, u1;
         plan.user_range(a_lo, a_hi, u0, u1);
         char *slot = ring + (size_t)(b % kSlots) * slot_bytes;
@@ -473,7 +487,7 @@ struct MapStream {
         for (int i = 0; i < plan.n_user; ++i) {
           dev_user[i] = slot + (size_t)i * map_bytes;
           MG_CUDA(cudaMemcpyAsync(dev_user[i], static_cast<const char *>(plan.host_user[i]) +
-                                  (size_t)u0 * plan.user_plane * plan.elem, bytes, cudaMemcpyHostToDevice, up));
+                                  (size_t)(u0 - u_plane0) * plan.user_plane * plan.elem, bytes, cudaMemcpyHostToDevice, up));
         }
         h2d_bytes += (int64_t)bytes * plan.n_user;
         MG_CUDA(cudaEventRecord(landed[b], up));
@@ -610,6 +624,43 @@ int fw25_mapgen_slab(const fw25_medium *md, int32_t device, int32_t gx0, int32_t
                      fw25_mapset **out, double *stats_ms) {
   if (gx1 <= gx0 || u_planes <= 0) { g_err = "fw25_mapgen_slab: empty plane range"; return 1; }
   return mapgen_impl(md, device, gx0, gx1, u_plane0, u_planes, out, stats_ms);
+}
+
+// ---- the same, in the background: the set is allocated and its device pointers are valid at once (an engine can be
+// created on them), an uploader thread streams the user-grid planes block by block and generates the maps behind them
+struct fw25_mapjob {
+  fw25::MapStream *S = nullptr;
+};
+
+int fw25_mapgen_slab_begin(const fw25_medium *md, int32_t device, int32_t gx0, int32_t gx1, int32_t u_plane0,
+                           int32_t u_planes, fw25_mapset **view, fw25_mapjob **job) {
+  if (!md || !view || !job) { g_err = "fw25_mapgen_slab_begin: NULL argument"; return 1; }
+  *view = nullptr; *job = nullptr;
+  if (gx1 <= gx0 || u_planes <= 0) { g_err = "fw25_mapgen_slab_begin: empty plane range"; return 1; }
+  fw25::reap_wait();
+  std::unique_ptr<fw25::MapStream> S(new fw25::MapStream());
+  try {
+    S->start(md, device, 32, gx0, gx1, u_plane0, u_planes);
+  } catch (const MgFail &f) {
+    return f.code;
+  }
+  *view = S->plan.ms.get();
+  S->go();
+  *job = new fw25_mapjob{S.release()};
+  return 0;
+}
+
+int fw25_mapgen_finish(fw25_mapjob *job, fw25_mapset **out, double *stats_ms) {
+  if (!job || !out) { g_err = "fw25_mapgen_finish: NULL argument"; return 1; }
+  *out = nullptr;
+  double st[2] = {0, 0};
+  fw25_mapset *ms = fw25::mapstream_finish(job->S, st, nullptr);   // joins the uploader, waits for the last block
+  fw25::mapstream_destroy(job->S);                                  // (frees the set too if the job failed)
+  delete job;
+  if (!ms) return 2;
+  if (stats_ms) { stats_ms[0] = st[0]; stats_ms[1] = st[1]; }
+  *out = ms;
+  return 0;
 }
 
 int fw25_mapset_problem(const fw25_mapset *ms, fw25_problem *pb) {

@@ -50,6 +50,9 @@ SIGS = {
     "fw25_mapgen": (C.c_int, [C.POINTER(CMedium), C.c_int32, C.POINTER(C.c_void_p), _D]),
     "fw25_mapgen_slab": (C.c_int, [C.POINTER(CMedium), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                    C.POINTER(C.c_void_p), _D]),
+    "fw25_mapgen_slab_begin": (C.c_int, [C.POINTER(CMedium), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                         C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "fw25_mapgen_finish": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), _D]),
     "fw25_mapset_problem": (C.c_int, [C.c_void_p, C.POINTER(engine.CProblem)]),
     "fw25_mapset_read": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p]),
     "fw25_mapset_invalid_count": (C.c_int64, [C.c_void_p]),
@@ -290,26 +293,51 @@ def run_medium(spec: MediumSpec, pb, device: int = 0, device_ids=None):
 class MapSet:
     """Device-resident maps of one medium (fw25_mapset).  Keep it alive as long as an engine uses it."""
 
-    def __init__(self, spec: MediumSpec, device: int = 0, planes: tuple | None = None):
+    def __init__(self, spec: MediumSpec, device: int = 0, planes: tuple | None = None, background: bool = False):
         """planes = (gx0, gx1): build the extended x planes [gx0, gx1) only (one x-slab incl. its ghost planes,
-        fw25_mapgen_slab); spec.user_planes says which user-grid planes the host arrays hold."""
+        fw25_mapgen_slab); spec.user_planes says which user-grid planes the host arrays hold.  background=True
+        (fw25_mapgen_slab_begin): returns at once with the final device pointers -- an engine can be created on them --
+        while the maps are still being uploaded and generated; call wait() before anything steps on them."""
         self.spec = spec
         self.device = device
         md, keep, (self.d_table, self.dmap, self.ndmap) = marshal_medium(spec)
         h = C.c_void_p()
         ms = (C.c_double * 2)()
-        if planes is None and spec.user_planes is None:
+        self._job = None
+        if planes is None and spec.user_planes is None and not background:
             engine._check(_lib().fw25_mapgen(C.byref(md), device, C.byref(h), ms))
             self.shape = spec.extended_shape
         else:
             gx0, gx1 = planes if planes is not None else (0, spec.extended_shape[0])
             u0, un = spec.user_planes if spec.user_planes is not None else (0, spec.user_shape[0])
-            engine._check(_lib().fw25_mapgen_slab(C.byref(md), device, int(gx0), int(gx1), int(u0), int(un), C.byref(h), ms))
+            if background:
+                job = C.c_void_p()
+                engine._check(_lib().fw25_mapgen_slab_begin(C.byref(md), device, int(gx0), int(gx1), int(u0), int(un),
+                                                            C.byref(h), C.byref(job)))
+                self._job, self._keep = job, keep          # the host arrays stay alive until wait()
+            else:
+                engine._check(_lib().fw25_mapgen_slab(C.byref(md), device, int(gx0), int(gx1), int(u0), int(un),
+                                                      C.byref(h), ms))
             self.shape = (int(gx1) - int(gx0),) + tuple(spec.extended_shape[1:])
         del keep
         self._h = h
         self.upload_ms, self.kernel_ms = ms[0], ms[1]
-        self.invalid_count = int(_lib().fw25_mapset_invalid_count(h))
+        self.invalid_count = int(_lib().fw25_mapset_invalid_count(h)) if self._job is None else 0
+
+    def wait(self) -> None:
+        """background=True: block until every plane has been generated (fw25_mapgen_finish)."""
+        if self._job is None:
+            return
+        job, self._job = self._job, None
+        out = C.c_void_p()
+        ms = (C.c_double * 2)()
+        rc = _lib().fw25_mapgen_finish(job, C.byref(out), ms)
+        self._keep = None
+        if rc:
+            self._h = None                                   # a failed job has freed the set
+            engine._check(rc)
+        self.upload_ms, self.kernel_ms = ms[0], ms[1]
+        self.invalid_count = int(_lib().fw25_mapset_invalid_count(self._h))
 
     def fill(self, cpb: "engine.CProblem") -> None:
         """Point a fw25_problem at these maps (fw25_mapset_problem)."""
@@ -331,6 +359,11 @@ class MapSet:
         return out
 
     def close(self) -> None:
+        if getattr(self, "_job", None) is not None and engine._lib is not None:
+            try:
+                self.wait()
+            except engine.EngineError:
+                pass
         if getattr(self, "_h", None) and engine._lib is not None:
             engine._lib.fw25_mapset_destroy(self._h)
             self._h = None

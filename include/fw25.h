@@ -220,6 +220,15 @@ int fw25_mapgen(const fw25_medium *md, int32_t device, fw25_mapset **out, double
  * m_spatial_order + n_pml_layer + n_transition_layer.  The values are those fw25_mapgen gives the same planes. */
 int fw25_mapgen_slab(const fw25_medium *md, int32_t device, int32_t gx0, int32_t gx1, int32_t u_plane0, int32_t u_planes,
                      fw25_mapset **out, double *stats_ms);
+/* fw25_mapgen_slab in the background.  _begin allocates the set and returns at once: `*view` already carries the final
+ * device pointers (fw25_mapset_problem / fw25_create may use them -- creating an engine never reads map contents), while
+ * an uploader thread streams the user-grid planes block by block and generates the maps behind them.  _finish waits for
+ * the last block, hands the set over (`*out` == the view) and destroys the job; nothing may STEP on the maps before it
+ * returns.  The host arrays of `md` must stay alive until then; `md` itself need not. */
+typedef struct fw25_mapjob fw25_mapjob;
+int fw25_mapgen_slab_begin(const fw25_medium *md, int32_t device, int32_t gx0, int32_t gx1, int32_t u_plane0,
+                           int32_t u_planes, fw25_mapset **view, fw25_mapjob **job);
+int fw25_mapgen_finish(fw25_mapjob *job, fw25_mapset **out, double *stats_ms);
 /* Fills nX nY nZ (the EXTENDED grid; nX = the planes held, for a slab), the 13 map pointers, dcmap, maps_on_device, map_pitch and dcmap_full3d of `pb`
  * so that fw25_create adopts the maps without a copy.  The mapset must outlive every engine created from it. */
 int fw25_mapset_problem(const fw25_mapset *ms, fw25_problem *pb);

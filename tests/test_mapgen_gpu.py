@@ -92,6 +92,55 @@ def test_slab_maps_equal_the_planes_of_the_whole_grid(name):
             mapgen.MapSet(short, planes=(0, ex))
 
 
+@pytest.mark.parametrize("name", ["m3d_big", "m2d_big", "m3d_lut"])
+def test_background_generation_equals_the_blocking_call(name):
+    """fw25_mapgen_slab_begin / fw25_mapgen_finish: the set's device pointers are final at once (an engine is created on
+    them while the planes are still being uploaded, block by block, and generated behind the copies); after wait() the maps
+    are byte-identical to the blocking builder's, for the whole grid and for a slab fed from a plane range."""
+    import dataclasses
+    g = np.load(GOLD / f"mapgen_{name}.npz")
+    spec = spec_of(name, g)
+    c = np.asarray(spec.sound_speed)
+    spec.extra.update(c_min=float(c.min()), c_max=float(c.max()))
+    with mapgen.MapSet(spec) as whole:
+        want = device_maps_of(whole)
+    with mapgen.MapSet(spec, background=True) as ms:
+        ptrs = ms.device_maps()
+        ms.wait()
+        assert ms.device_maps()["rho"] == ptrs["rho"] and ms.shape == spec.extended_shape and ms.upload_ms >= 0
+        got = device_maps_of(ms)
+    for stem in MAP_NAMES + ("dcmap",):
+        assert np.array_equal(got[stem], want[stem]), stem
+    nb, ex, ux = spec.num_boundary_points, spec.extended_shape[0], spec.user_shape[0]
+    lo, hi = ex // 3, ex - 2
+    u0, u1 = min(max(lo - nb, 0), ux - 1), min(max(hi - 1 - nb, 0), ux - 1) + 1
+    cut = lambda a: None if a is None else np.ascontiguousarray(np.asarray(a)[u0:u1])   # noqa: E731
+    part = dataclasses.replace(spec, sound_speed=cut(spec.sound_speed), density=cut(spec.density), beta=cut(spec.beta),
+                               relax=None if spec.relax is None else {k: cut(v) for k, v in spec.relax.items()},
+                               alpha_coeff=cut(spec.alpha_coeff), alpha_power=cut(spec.alpha_power),
+                               user_planes=(u0, u1 - u0))
+    with mapgen.MapSet(part, planes=(lo, hi), background=True) as ms:
+        got = device_maps_of(ms) if (ms.wait() or True) else None
+    for stem in MAP_NAMES + ("dcmap",):
+        assert np.array_equal(got[stem], want[stem][lo:hi]), stem
+
+
+def test_engine_created_while_the_maps_are_still_arriving(monkeypatch):
+    """An engine created on a background map set before wait() steps to the same frames as one created afterwards."""
+    from tests.test_pipeline import sequential, spec_and_problem
+    spec, pb = spec_and_problem((112, 24, 30), n_pml=5, n_trans=3, nT=20, modT=2, seed=44)
+    want, _ = sequential(spec, pb)
+    with mapgen.MapSet(spec, background=True) as ms:
+        eng = engine.Engine(pb, device=0, device_maps=ms.device_maps())
+        try:
+            ms.wait()
+            got, _ = eng.run()
+        finally:
+            eng.close()
+    np.testing.assert_array_equal(got, want)
+    assert np.abs(want).max() > 0
+
+
 def test_lookup_counts_invalid_entries():
     g = np.load(GOLD / "mapgen_m2d_lut.npz")
     spec = spec_of("m2d_lut", g)
