@@ -104,7 +104,8 @@ void mapstream_go(MapStream *S);                                                
 int mapstream_blocks(const MapStream *S);
 cudaEvent_t mapstream_wait_recorded(MapStream *S, int block);
 fw25_mapset *mapstream_finish(MapStream *S, double *stats_ms, int64_t *h2d_bytes);
-void mapstream_destroy(MapStream *S);
+void mapstream_join(MapStream *S);      // the uploader thread is gone: nothing reads the caller's host arrays any more
+void mapstream_destroy(MapStream *S);   // joins too; frees the upload ring (a synchronising cudaFree), streams, events
 
 // point kernels: fw25_points.cu
 void launch_dcmap_mask(int32_t *dcmap, long long cells, int pitch, int nC, int nB, long long first_plane,

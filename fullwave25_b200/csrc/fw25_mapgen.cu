@@ -554,6 +554,9 @@ fw25_mapset *mapstream_finish(MapStream *S, double *stats_ms, int64_t *h2d_bytes
   if (h2d_bytes) *h2d_bytes = S->h2d_bytes;
   return S->plan.ms.release();
 }
+void mapstream_join(MapStream *S) {
+  if (S->th.joinable()) S->th.join();
+}
 void mapstream_destroy(MapStream *S) { delete S; }
 
 }  // namespace fw25
