@@ -104,6 +104,7 @@ void mapstream_go(MapStream *S);                                                
 int mapstream_blocks(const MapStream *S);
 cudaEvent_t mapstream_wait_recorded(MapStream *S, int block);
 fw25_mapset *mapstream_finish(MapStream *S, double *stats_ms, int64_t *h2d_bytes);
+void mapstream_bequeath(MapStream *S, fw25_mapset *ms);   // after _finish: the stream's device scratch is freed with the set
 void mapstream_join(MapStream *S);      // the uploader thread is gone: nothing reads the caller's host arrays any more
 void mapstream_destroy(MapStream *S);   // joins too; frees the upload ring (a synchronising cudaFree), streams, events
 

@@ -228,8 +228,11 @@ struct fw25_mapset {
   float *maps[13] = {};
   int32_t *dcmap = nullptr;
   long long invalid = 0;
+  std::vector<void *> attic;   // device scratch of the job that built the set (upload ring, tables), released with the set:
+                               // a cudaFree synchronises the device and would sit in front of the run's first step
   ~fw25_mapset() {
     cudaSetDevice(device);
+    for (void *p : attic) cudaFree(p);
     if (block) cudaFree(block);
   }
 };
@@ -554,6 +557,10 @@ fw25_mapset *mapstream_finish(MapStream *S, double *stats_ms, int64_t *h2d_bytes
   if (h2d_bytes) *h2d_bytes = S->h2d_bytes;
   return S->plan.ms.release();
 }
+void mapstream_bequeath(MapStream *S, fw25_mapset *ms) {
+  if (S->ring) { ms->attic.push_back(S->ring); S->ring = nullptr; }
+  if (S->plan.tables) { ms->attic.push_back(S->plan.tables); S->plan.tables = nullptr; }
+}
 void mapstream_join(MapStream *S) {
   if (S->th.joinable()) S->th.join();
 }
@@ -658,6 +665,7 @@ int fw25_mapgen_finish(fw25_mapjob *job, fw25_mapset **out, double *stats_ms) {
   *out = nullptr;
   double st[2] = {0, 0};
   fw25_mapset *ms = fw25::mapstream_finish(job->S, st, nullptr);   // joins the uploader, waits for the last block
+  if (ms) fw25::mapstream_bequeath(job->S, ms);                     // the ring and the tables are freed with the set
   fw25::mapstream_destroy(job->S);                                  // (frees the set too if the job failed)
   delete job;
   if (!ms) return 2;
