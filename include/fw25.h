@@ -224,7 +224,9 @@ int fw25_mapgen_slab(const fw25_medium *md, int32_t device, int32_t gx0, int32_t
  * device pointers (fw25_mapset_problem / fw25_create may use them -- creating an engine never reads map contents), while
  * an uploader thread streams the user-grid planes block by block and generates the maps behind them.  _finish waits for
  * the last block, hands the set over (`*out` == the view) and destroys the job; nothing may STEP on the maps before it
- * returns.  The host arrays of `md` must stay alive until then; `md` itself need not. */
+ * returns.  The host arrays of `md` must stay alive until then; `md` itself need not.  The job's device scratch (an
+ * upload ring of 3 x 32 user-grid planes per map) stays with the set and is released by fw25_mapset_destroy: freeing
+ * device memory synchronises the device and would sit between map generation and the first time step. */
 typedef struct fw25_mapjob fw25_mapjob;
 int fw25_mapgen_slab_begin(const fw25_medium *md, int32_t device, int32_t gx0, int32_t gx1, int32_t u_plane0,
                            int32_t u_planes, fw25_mapset **view, fw25_mapjob **job);
