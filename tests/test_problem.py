@@ -132,3 +132,24 @@ def test_problem_for_device_resident_maps():
     air = np.zeros((30, 32, 34), bool)
     air[3, 4, 5] = True
     assert Problem.for_device_maps(ms, grid, src, sen, air_map=air).icczero.tolist() == [[3, 4, 5]]
+
+
+def test_parallel_cast_equals_numpy_cast():
+    """`cast_c` (row blocks converted by a thread pool) returns exactly what `np.ascontiguousarray(a, dtype)` returns."""
+    from fullwave25_b200 import problem
+    rng = np.random.default_rng(7)
+    big = rng.standard_normal((3000, 3001)) * 1e3                 # above the parallel threshold
+    assert big.size >= problem._CAST_PARALLEL_MIN
+    cases = [big, np.asfortranarray(big), big[::2, 1::3], big.astype(np.float32)[:, ::2],
+             rng.integers(-5, 2**31 - 1, (3_000_000, 3)), rng.standard_normal((5, 7)), np.float64(3.5),
+             rng.standard_normal((1, 9_000_000))]
+    for a in cases:
+        for dt in (np.float32, np.int32):
+            if dt is np.int32 and np.asarray(a).dtype.kind == "f":
+                continue
+            got = problem.cast_c(a, dt)
+            want = np.ascontiguousarray(a, dtype=dt)
+            assert got.dtype == want.dtype and got.shape == want.shape and got.flags["C_CONTIGUOUS"]
+            np.testing.assert_array_equal(got, want)
+    same = np.zeros((4, 5), np.float32)
+    assert problem.cast_c(same, np.float32) is same               # nothing to do: no copy
