@@ -13,8 +13,11 @@ Our arm: one process per GPU (torchrun for N > 1), libfw25.so kernels, NCCL halo
   value        K steps timed with CUDA events, maps resident in HBM, max over ranks
   roofline     the dominant sweep kernel against the measured HBM copy bandwidth (N = 1), traffic from the committed ncu capture
   e2e          N = 1: the whole job through `fw25_run_medium` (C-ABI) from the USER-grid medium in pinned host memory --
-               allocation, host->device copies, map generation, K steps, frames back, free -- checked bit for bit against
-               the sequential path; `hostmaps_variant` (and N > 1): the 14 engine maps uploaded from pinned host memory
+               allocation, host->device copies, map generation, K steps, frames back on the host (the device memory is
+               given back by a reaper thread after the call has returned) -- checked bit for bit against the sequential
+               path; N > 1: every rank uploads the user-grid planes of its slab and builds its slab of the maps on its GPU
+               (`fw25_mapgen_slab_begin / _finish`), NCCL halos, frames gathered on rank 0; `hostmaps_variant`: the 14
+               engine maps uploaded from pinned host memory (round 1's path)
   same_grid    our rate on the grid the reference arm runs (the largest it can hold), in the reference binary's own dcmap
                mode, with the sha256 of the sensor frames: equal to the reference arm's `genout_sha256` = bit-identical
   parity_n_vs_1 (N > 1) N ranks vs rank 0 alone on a mid-size grid with sources / sensors / air voxels ON the interfaces
